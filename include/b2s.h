@@ -1,0 +1,112 @@
+/*
+ * b2s.h -- C ABI of libb200stft.so, the B200 (sm_100a) spectrogram engine.
+ *
+ * This is the drop-in boundary for ONE path of Karmotr1ne/Spectrogram-Generator:
+ * the per-sweep spectrogram
+ *
+ *     f, t, Sxx = spectrogram(data, fs=fs, nperseg=nperseg,
+ *                             scaling="density", mode="psd")
+ *
+ * made at /root/reference/PlotEngine.py:113 (plot) and :232 (HMM features),
+ * imported at PlotEngine.py:8.  The reference's boundary is that Python call
+ * (there is no FFI in the reference); the entry points below are what a
+ * Python/ctypes shim behind that call binds, and each one
+ * names the reference / SciPy code whose work it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every *device* pointer is owned by the
+ *    caller (PyTorch tensors in the shipped host code);
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    all work is enqueued on it and nothing synchronises unless stated;
+ *  - return value: 0 = success, <0 = error (B2S_ERR_*), text via
+ *    b2s_last_error() (thread-local);
+ *  - the library keeps one small device cache: twiddle tables keyed by
+ *    (device, nperseg).  It allocates nothing else persistent.
+ *  - there is no CPU fallback: without a CUDA device every compute entry
+ *    returns B2S_ERR_CUDA.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_ABI_VERSION 1
+
+#define B2S_OK 0
+#define B2S_ERR_BAD_ARG (-1)     /* invalid argument (mirrors SciPy's ValueError cases) */
+#define B2S_ERR_UNSUPPORTED (-2) /* nperseg not handled by this entry */
+#define B2S_ERR_CUDA (-3)        /* CUDA runtime error; see b2s_last_error() */
+
+#define B2S_OUT_LINEAR 0 /* PSD / power spectrum, linear */
+#define B2S_OUT_DB 1     /* 10*log10(max(S, db_floor)) */
+
+int b2s_version(void);
+const char* b2s_last_error(void);
+
+/* 1 if `nperseg` runs on the fused radix-16 Stockham kernel (powers of two in
+ * [32, 16384]), 2 if it runs on the direct-DFT kernel (any other 2..8192:
+ * the GUI spin box allows any integer 32..8192, GUI.py:87-89, and SciPy clamps
+ * nperseg to len(x), _spectral_py.py:2443-2447), 0 if unsupported. */
+int b2s_nperseg_support(int nperseg);
+
+/* Frames SciPy produces for a signal of n samples: (n - nperseg)//hop + 1
+ * (sliding_window_view(...)[..., ::step, :], _spectral_py.py:2377-2381). */
+long long b2s_frame_count(long long n, int nperseg, int hop);
+
+/*
+ * The hot path.  Replaces, for real input, `_fft_helper` (_spectral_py.py:
+ * 2346-2397: framing, detrend, window, rfft) and the PSD epilogue of
+ * `_spectral_helper` (_spectral_py.py:2313-2322: conj(X)*X, *= scale, one-sided
+ * doubling) -- i.e. everything the call at PlotEngine.py:113/232 computes
+ * except the two axis arrays (host side, bit-exact recipes).
+ *
+ *   x                 device, [batch][n] samples; signal b starts at x + b*x_batch_stride
+ *   nperseg, hop      frame length and step (hop = nperseg - noverlap)
+ *   window            device, nperseg fp32 taps (built on the host in float64
+ *                     with SciPy's recipe, rounded once)
+ *   detrend           0 = False, 1 = 'constant' (per-frame mean removal,
+ *                     _signaltools.py:4288-4290)
+ *   scale             1/(fs*sum(w^2)) for scaling='density', 1/sum(w)^2 for
+ *                     'spectrum' (_spectral_py.py:2274-2277), computed in double
+ *   out_mode/db_floor B2S_OUT_LINEAR, or B2S_OUT_DB with a linear floor
+ *   kmin,kmax         inclusive bin crop (0, nperseg/2 for all bins); the
+ *                     reference masks bins to [fmin,fmax] right after the call
+ *                     (PlotEngine.py:114-115)
+ *   frame0,nframes    frame range [frame0, frame0+nframes) of every signal
+ *                     (time-chunking: a rank computes its own range; frame j
+ *                     covers samples [j*hop, j*hop+nperseg))
+ *   out               device, [batch][nframes][kmax-kmin+1] fp32; signal b at
+ *                     out + b*out_batch_stride.  [frame][bin] is the layout of
+ *                     SciPy's own result buffer (Sxx is its transposed view).
+ */
+int b2s_stft_psd_f32(const float* x, long long batch, long long n, long long x_batch_stride,
+                     int nperseg, int hop, const float* window, int detrend, double scale,
+                     int out_mode, float db_floor, int kmin, int kmax,
+                     long long frame0, long long nframes,
+                     float* out, long long out_batch_stride, void* stream);
+
+/* Same, float64 samples in device memory (converted to fp32 on load; SciPy's
+ * dtype rule `result_type(x, complex64)`, _spectral_py.py:2169, is honoured by
+ * the host shim, which widens the fp32 result when x is float64). */
+int b2s_stft_psd_f64(const double* x, long long batch, long long n, long long x_batch_stride,
+                     int nperseg, int hop, const float* window, int detrend, double scale,
+                     int out_mode, float db_floor, int kmin, int kmax,
+                     long long frame0, long long nframes,
+                     float* out, long long out_batch_stride, void* stream);
+
+/*
+ * Cross-sweep sum / mean (BASELINE config 2; the reference has no code for it,
+ * SURVEY.md 8 a-15): out[e] = post_scale * sum_b in[b*in_batch_stride + e],
+ * summed in a fixed order (deterministic).  `scratch` must hold
+ * b2s_batch_sum_scratch_elems(batch, elems) floats (may be NULL when that is 0).
+ */
+long long b2s_batch_sum_scratch_elems(long long batch, long long elems);
+int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long long in_batch_stride,
+                      float* out, float* scratch, float post_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

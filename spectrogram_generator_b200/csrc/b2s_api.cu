@@ -1,0 +1,206 @@
+// C ABI of libb200stft.so (include/b2s.h): argument checking, twiddle cache,
+// launch configuration.  No torch types, no allocations other than the
+// per-(device, nperseg) twiddle tables.
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/b2s.h"
+#include "b2s_host.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(B2S_ERR_CUDA, std::string("b2s: CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int smem_optin = 0;
+};
+
+std::mutex g_mu;
+std::map<int, DeviceInfo> g_dev;
+std::map<std::pair<int, int>, float2*> g_tw;     // (device, nperseg) -> W_N table
+
+int device_info(DeviceInfo& out, int& dev) {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_dev.find(dev);
+    if (it == g_dev.end()) {
+        DeviceInfo di;
+        e = cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+        e = cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+        it = g_dev.emplace(dev, di).first;
+    }
+    out = it->second;
+    return B2S_OK;
+}
+
+// Twiddle table for nperseg on the current device; built on the host in double,
+// uploaded once (synchronously, first use only) and cached for the process.
+int twiddles(int dev, int nperseg, const float2** out) {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto key = std::make_pair(dev, nperseg);
+    auto it = g_tw.find(key);
+    if (it == g_tw.end()) {
+        std::vector<float> host;
+        b2s::make_twiddles(nperseg, host);
+        float2* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
+        e = cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(e, "cudaMemcpy(twiddles)");
+        }
+        it = g_tw.emplace(key, d).first;
+    }
+    *out = it->second;
+    return B2S_OK;
+}
+
+template <int LOG2N, typename Tin>
+int launch_stft(const b2s::StftArgs& a, cudaStream_t stream) {
+    using PL = b2s::Plan<LOG2N>;
+    constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
+    auto kern = b2s::stft_psd_kernel<LOG2N, Tin, MINB>;
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+
+    static thread_local int configured_dev = -1;   // per instantiation
+    static thread_local int occ = 0;
+    if (configured_dev != dev) {
+        if ((int)PL::SMEM > di.smem_optin)
+            return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this nperseg");
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PL::NT, PL::SMEM);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+        if (occ < 1) occ = 1;
+        configured_dev = dev;
+    }
+    const long long resident_ctas = (long long)di.sm_count * occ;
+
+    b2s::StftParams p{};
+    std::string err;
+    rc = b2s::plan_stft(a, PL::FPC, resident_ctas * PL::FPC, p, err);
+    if (rc < 0) return fail(rc, err);
+    if (p.n_units == 0) return B2S_OK;
+    rc = twiddles(dev, a.nperseg, &p.tw);
+    if (rc != B2S_OK) return rc;
+
+    // persistent grid: a whole number of waves, never more CTAs than work
+    long long need = (p.n_units + PL::FPC - 1) / PL::FPC;
+    long long grid = (need < resident_ctas) ? need : resident_ctas;
+    kern<<<(unsigned)grid, PL::NT, PL::SMEM, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "stft_psd_kernel launch");
+    return B2S_OK;
+}
+
+template <typename Tin>
+int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
+               const float* window, int detrend, double scale, int out_mode, float db_floor, int kmin,
+               int kmax, long long frame0, long long nframes, float* out, long long out_batch_stride,
+               void* stream) {
+    b2s::StftArgs a{x, (int)(sizeof(Tin) == 8), batch, n, x_batch_stride, nperseg, hop, window, detrend,
+                    scale, out_mode, db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride};
+    // validate before touching the device so bad arguments are reported as such
+    {
+        b2s::StftParams p{};
+        std::string err;
+        int rc = b2s::plan_stft(a, 1, 1, p, err);
+        if (rc < 0) return fail(rc, err);
+    }
+    const int log2n = b2s::ilog2_exact(nperseg);
+    int rc = B2S_ERR_UNSUPPORTED;
+#define B2S_RUN(L) rc = launch_stft<L, Tin>(a, (cudaStream_t)stream)
+    B2S_DISPATCH_LOG2N(log2n, B2S_RUN)
+#undef B2S_RUN
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2s_version(void) { return B2S_ABI_VERSION; }
+
+const char* b2s_last_error(void) { return g_err.c_str(); }
+
+int b2s_nperseg_support(int nperseg) {
+    const int l = b2s::ilog2_exact(nperseg);
+    if (l >= 5 && l <= 14) return 1;
+    return 0;
+}
+
+long long b2s_frame_count(long long n, int nperseg, int hop) {
+    if (nperseg < 1 || hop < 1) return 0;
+    return b2s::frames_available(n, nperseg, hop);
+}
+
+int b2s_stft_psd_f32(const float* x, long long batch, long long n, long long x_batch_stride, int nperseg,
+                     int hop, const float* window, int detrend, double scale, int out_mode, float db_floor,
+                     int kmin, int kmax, long long frame0, long long nframes, float* out,
+                     long long out_batch_stride, void* stream) {
+    return stft_entry<float>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
+                             db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, stream);
+}
+
+int b2s_stft_psd_f64(const double* x, long long batch, long long n, long long x_batch_stride, int nperseg,
+                     int hop, const float* window, int detrend, double scale, int out_mode, float db_floor,
+                     int kmin, int kmax, long long frame0, long long nframes, float* out,
+                     long long out_batch_stride, void* stream) {
+    return stft_entry<double>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
+                              db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, stream);
+}
+
+static const int kSumSlabRows = 64;
+
+long long b2s_batch_sum_scratch_elems(long long batch, long long elems) {
+    if (batch <= kSumSlabRows) return 0;
+    const long long slabs = (batch + kSumSlabRows - 1) / kSumSlabRows;
+    return slabs * elems;
+}
+
+int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long long in_batch_stride,
+                      float* out, float* scratch, float post_scale, void* stream) {
+    if (!in || !out || batch < 1 || elems < 1 || in_batch_stride < elems || batch > 0x7fffffffLL)
+        return fail(B2S_ERR_BAD_ARG, "b2s_batch_sum_f32: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int block = 256;
+    const unsigned gx = (unsigned)((elems + block - 1) / block);
+    if (batch <= kSumSlabRows) {
+        b2s::batch_sum_kernel<<<dim3(gx, 1), block, 0, st>>>(in, in_batch_stride, (int)batch, (int)batch, elems,
+                                                              out, post_scale);
+    } else {
+        if (!scratch) return fail(B2S_ERR_BAD_ARG, "b2s_batch_sum_f32: scratch required for batch > 64");
+        const long long slabs = (batch + kSumSlabRows - 1) / kSumSlabRows;
+        b2s::batch_sum_kernel<<<dim3(gx, (unsigned)slabs), block, 0, st>>>(in, in_batch_stride, (int)batch,
+                                                                          kSumSlabRows, elems, scratch, 1.0f);
+        b2s::batch_sum_kernel<<<dim3(gx, 1), block, 0, st>>>(scratch, elems, (int)slabs, (int)slabs, elems, out,
+                                                              post_scale);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
+    return B2S_OK;
+}
+
+}  // extern "C"

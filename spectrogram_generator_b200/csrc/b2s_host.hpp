@@ -1,0 +1,138 @@
+// Host-side launch planning shared by the CUDA library (b2s_api.cu) and the
+// CPU emulator harness (tests/emu).  Plain C++: no CUDA runtime calls here.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/b2s.h"
+#include "b2s_kernels.cuh"
+
+namespace b2s {
+
+// The arguments of the C-ABI entry b2s_stft_psd_* (include/b2s.h).
+struct StftArgs {
+    const void* x;
+    int x_is_f64;
+    long long batch, n, x_batch_stride;
+    int nperseg, hop;
+    const float* window;
+    int detrend;
+    double scale;
+    int out_mode;
+    float db_floor;
+    int kmin, kmax;
+    long long frame0, nframes;
+    float* out;
+    long long out_batch_stride;
+};
+
+inline int ilog2_exact(int v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+// W_N^j = exp(-2 pi i j / N), j = 0..N-1, computed in double and rounded once.
+inline void make_twiddles(int N, std::vector<float>& out) {
+    out.resize(2 * (size_t)N);
+    for (int j = 0; j < N; ++j) {
+        const double a = 2.0 * M_PI * (double)j / (double)N;
+        out[2 * j] = (float)std::cos(a);
+        out[2 * j + 1] = (float)(-std::sin(a));
+    }
+}
+
+inline long long frames_available(long long n, int nperseg, int hop) {
+    return (n < nperseg) ? 0 : (n - nperseg) / hop + 1;
+}
+
+// Validates the arguments and fills the kernel parameter block (everything
+// except the device twiddle pointer).  `resident_groups` is how many frame
+// groups the launch can keep resident (grid * groups per CTA); it sizes the
+// work units so that every group gets several runs of consecutive frames.
+inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_groups, StftParams& p,
+                     std::string& err) {
+    const int log2n = ilog2_exact(a.nperseg);
+    if (a.nperseg < 1 || a.hop < 1 || a.batch < 0 || a.nframes < 0 || a.n < 0) {
+        err = "b2s: nperseg, hop must be >= 1 and sizes non-negative";
+        return B2S_ERR_BAD_ARG;
+    }
+    if (log2n < 5 || log2n > 14) {
+        err = "b2s: this entry handles power-of-two nperseg in [32, 16384]";
+        return B2S_ERR_UNSUPPORTED;
+    }
+    if (!a.x || !a.window || !a.out) {
+        err = "b2s: null pointer";
+        return B2S_ERR_BAD_ARG;
+    }
+    const int K = a.nperseg / 2 + 1;
+    if (a.kmin < 0 || a.kmax >= K || a.kmin > a.kmax) {
+        err = "b2s: bin crop [kmin,kmax] outside [0, nperseg/2]";
+        return B2S_ERR_BAD_ARG;
+    }
+    if (a.frame0 < 0 || a.frame0 + a.nframes > frames_available(a.n, a.nperseg, a.hop)) {
+        err = "b2s: frame range exceeds (n - nperseg)//hop + 1";
+        return B2S_ERR_BAD_ARG;
+    }
+    if (a.nframes > 0x7fffffffLL || a.batch > 0x7fffffffLL) {
+        err = "b2s: nframes/batch too large for one launch";
+        return B2S_ERR_BAD_ARG;
+    }
+    const int kout = a.kmax - a.kmin + 1;
+    if (a.batch > 1 && (a.x_batch_stride < a.n || a.out_batch_stride < a.nframes * (long long)kout)) {
+        err = "b2s: batch strides overlap";
+        return B2S_ERR_BAD_ARG;
+    }
+    p.x = a.x;
+    p.x_batch_stride = a.x_batch_stride;
+    p.frame0 = a.frame0;
+    p.out_batch_stride = a.out_batch_stride;
+    p.window = a.window;
+    p.tw = nullptr;
+    p.out = a.out;
+    p.nframes = (int)a.nframes;
+    p.hop = a.hop;
+    p.detrend = a.detrend ? 1 : 0;
+    p.out_mode = a.out_mode ? 1 : 0;
+    p.kmin = a.kmin;
+    p.kmax = a.kmax;
+    p.scale = (float)a.scale;
+    p.db_floor = a.db_floor;
+    // vector loads need every frame start on a 2-element boundary
+    const size_t esz = a.x_is_f64 ? 8 : 4;
+    const bool base_ok = (reinterpret_cast<uintptr_t>(a.x) % (2 * esz)) == 0;
+    p.vec_ok = (base_ok && (a.hop % 2 == 0) && (a.x_batch_stride % 2 == 0 || a.batch <= 1)) ? 1 : 0;
+    // work units: runs of consecutive frames of one signal
+    long long total = a.batch * a.nframes;
+    long long want_units = resident_groups * 4;
+    long long cf = (want_units > 0) ? (total + want_units - 1) / want_units : a.nframes;
+    if (cf < 1) cf = 1;
+    if (cf > 64) cf = 64;
+    if (cf > a.nframes) cf = a.nframes > 0 ? a.nframes : 1;
+    p.chunk_frames = (int)cf;
+    p.units_per_signal = (a.nframes + cf - 1) / cf;
+    p.n_units = p.units_per_signal * a.batch;
+    (void)groups_per_cta;
+    return log2n;
+}
+
+#define B2S_DISPATCH_LOG2N(log2n, F)   \
+    switch (log2n) {                   \
+        case 5: F(5); break;           \
+        case 6: F(6); break;           \
+        case 7: F(7); break;           \
+        case 8: F(8); break;           \
+        case 9: F(9); break;           \
+        case 10: F(10); break;         \
+        case 11: F(11); break;         \
+        case 12: F(12); break;         \
+        case 13: F(13); break;         \
+        case 14: F(14); break;         \
+        default: break;                \
+    }
+
+}  // namespace b2s

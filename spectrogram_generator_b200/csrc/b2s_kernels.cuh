@@ -1,0 +1,335 @@
+// Fused STFT -> one-sided PSD kernels for sm_100a (power-of-two nperseg).
+//
+// One launch does everything `_fft_helper` + the PSD epilogue of SciPy's
+// `_spectral_helper` do on the CPU (scipy/signal/_spectral_py.py:2374-2395 and
+// :2313-2322), i.e. the path the reference takes at PlotEngine.py:113/232:
+//
+//   frame gather -> per-frame mean removal -> window -> real FFT
+//   -> |X|^2 * scale (x2 on interior bins) -> optional 10*log10(max(.,floor))
+//   -> [frame][bin] store (optionally cropped to [kmin,kmax]).
+//
+// Structure (see DESIGN.md "Kernel K-STFT"):
+//   * the N real samples of a frame are packed as M = N/2 complex points;
+//     a "group" of G = M/16 threads owns a run of consecutive frames of one
+//     signal, every thread holding 16 complex points in registers;
+//   * M = 16^P * g: P radix-16 Stockham passes (first one straight from the
+//     global loads, window/detrend applied in registers) exchanged through a
+//     padded shared-memory buffer private to the group, then a fused final
+//     stage that does the last radix-g butterflies *and* the real-FFT
+//     split (X[k], X[M-k] from Z[k], Z[M-k]) *and* the PSD epilogue, and
+//     stores straight to global memory, coalesced over bins;
+//   * groups of <= 32 threads synchronise with __syncwarp(group mask) only.
+//
+// The file compiles for the CPU SIMT emulator (tests/emu) when B2S_EMU is
+// defined; that build is test tooling, never a product path.
+#pragma once
+
+#include "b2s_fft.cuh"
+
+namespace b2s {
+
+struct StftParams {
+    const void* x;               // [batch][n] samples (float or double), device
+    long long x_batch_stride;    // elements between signals
+    long long n_units;           // work units = batch * units_per_signal
+    long long units_per_signal;  // ceil(nframes / chunk_frames)
+    long long frame0;            // first (global) frame index of this launch
+    long long out_batch_stride;  // elements between signals in `out`
+    const float* window;         // [nperseg] fp32 window table, device
+    const float2* tw;            // [nperseg] W_N^j = (cos, -sin)(2 pi j / N), device
+    float* out;                  // [batch][nframes][kmax-kmin+1]
+    int nframes;                 // frames per signal computed by this launch
+    int chunk_frames;            // consecutive frames per work unit
+    int hop;
+    int detrend;                 // 0 none, 1 constant
+    int out_mode;                // 0 linear power, 1 dB
+    int kmin, kmax;              // inclusive bin crop
+    int vec_ok;                  // 1: frame starts are 2-element aligned (vector loads)
+    float scale;                 // 1/(fs*sum(w^2))  or  1/sum(w)^2
+    float db_floor;              // linear floor applied before log10 in dB mode
+};
+
+template <int LOG2N>
+struct Plan {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int M = N / 2;
+    static constexpr int G = (M / 16 > 0) ? M / 16 : 1;          // threads per frame
+    static constexpr int P = (M >= 4096) ? 3 : ((M >= 256) ? 2 : 1);
+    static constexpr int NS = (P == 1) ? 16 : ((P == 2) ? 256 : 4096);
+    static constexpr int GF = M / NS;                            // final radix 1,2,4,8
+    static constexpr int NT = (G > 256) ? G : 256;               // threads per CTA
+    static constexpr int FPC = NT / G;                           // groups per CTA
+    static constexpr int TPT = (NS / 2) / G;                     // final tasks per thread
+    static constexpr int BUF = M + (M >> 4) * 2;                 // padded complex slots
+    static constexpr int RED = (G > 32) ? G / 32 : 1;            // mean partials per group
+    static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * 2 * RED * sizeof(float);
+    static_assert(M >= 16, "nperseg >= 32");
+    static_assert(GF == 1 || GF == 2 || GF == 4 || GF == 8, "plan");
+};
+
+// padded index inside a group's exchange buffer (16 B pad every 128 B)
+B2S_HD int phys(int e) { return e + ((e >> 4) << 1); }
+
+// ---- group synchronisation -------------------------------------------------
+template <int G>
+B2S_DEVICE void group_sync(unsigned gmask, int grp) {
+    if constexpr (G <= 32) {
+        __syncwarp(gmask);
+    } else {
+        b2s_bar_sync(grp + 1, G);      // named barrier private to the group
+    }
+}
+
+template <typename Tin> struct Loader;
+template <> struct Loader<float> {
+    B2S_DEVICE static float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+    B2S_DEVICE static float ld1(const float* p) { return __ldg(p); }
+};
+template <> struct Loader<double> {
+    B2S_DEVICE static float2 ld2(const double* p) {
+        const double2 d = __ldg(reinterpret_cast<const double2*>(p));
+        return cmk((float)d.x, (float)d.y);
+    }
+    B2S_DEVICE static float ld1(const double* p) { return (float)__ldg(p); }
+};
+
+// ---- epilogue helpers ---------------------------------------------------------
+struct Epi {
+    float* row;        // out + frame row (already offset by -kmin)
+    float s_edge;      // scale            (DC / Nyquist)
+    float s_int;       // 2*scale          (interior bins)
+    float floor;
+    int kmin, kmax, db;
+    B2S_DEVICE void put(int k, float p) const {
+        if (db) p = 10.0f * log10f(fmaxf(p, floor));
+        if (k >= kmin && k <= kmax) row[k] = p;
+    }
+    // Z[k] = zk, Z[M-k] = zm, w = W_N^k : interior bins k and M-k
+    B2S_DEVICE void pair(int k, int mk, float2 zk, float2 zm, float2 w) const {
+        const float ex = zk.x + zm.x, ey = zk.y - zm.y;      // 2E = zk + conj(zm)
+        const float ox = zk.y + zm.y, oy = zm.x - zk.x;      // 2O = -i (zk - conj(zm))
+        const float tx = fmaf(-oy, w.y, ox * w.x);           // T = w * 2O
+        const float ty = fmaf(oy, w.x, ox * w.y);
+        const float ax = ex + tx, ay = ey + ty;              // 2 X[k]
+        const float bx = ex - tx, by = ey - ty;              // 2 conj(X[M-k])
+        put(k, 0.25f * s_int * fmaf(ax, ax, ay * ay));
+        put(mk, 0.25f * s_int * fmaf(bx, bx, by * by));
+    }
+    B2S_DEVICE void self_mid(int k, float2 z) const { put(k, s_int * fmaf(z.x, z.x, z.y * z.y)); }
+    B2S_DEVICE void dc_nyq(int M, float2 z0) const {
+        const float a = z0.x + z0.y, b = z0.x - z0.y;
+        put(0, s_edge * a * a);
+        put(M, s_edge * b * b);
+    }
+};
+
+// Mean over the N = 32 G samples a group holds (16 complex points per thread).
+// Deterministic: fixed pairwise tree per thread, xor-butterfly across lanes, fixed
+// order across warps.  `red` (RED floats per group) is only used when G > 32.
+template <int LOG2N>
+B2S_DEVICE float group_mean(const float2 (&v)[16], unsigned gmask, int grp, int j, unsigned lane, float* red) {
+    using PL = Plan<LOG2N>;
+    constexpr int G = PL::G;
+    float s[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[r] = v[r].x + v[r].y;
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int r = 0; r < w; ++r) s[r] += s[r + w];
+    float tot = s[0];
+#pragma unroll
+    for (int o = (G < 32 ? G : 32) / 2; o >= 1; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
+    if constexpr (G > 32) {
+        if (lane == 0) red[j >> 5] = tot;
+        group_sync<G>(gmask, grp);
+        tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < PL::RED; ++w) tot += red[w];
+    }
+    return tot * (1.0f / (float)PL::N);
+}
+
+// ---- the kernel ------------------------------------------------------------------
+template <int LOG2N, typename Tin, int MINB>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const StftParams p) {
+    using PL = Plan<LOG2N>;
+    constexpr int M = PL::M, G = PL::G, NS = PL::NS, GF = PL::GF;
+
+    B2S_DYN_SMEM(smem_raw);
+    const int tid = (int)threadIdx.x;
+    const int grp = tid / G;
+    const int j = tid - grp * G;
+    float2* const buf = reinterpret_cast<float2*>(smem_raw) + (size_t)grp * PL::BUF;
+    float* const red = reinterpret_cast<float*>(smem_raw + (size_t)PL::FPC * PL::BUF * sizeof(float2)) + grp * 2 * PL::RED;
+    const unsigned lane = (unsigned)tid & 31u;
+    const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(unsigned)(G - 1)));
+
+    // per-thread constants: the window taps this thread always multiplies by
+    float2 win[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(p.window) + (j + G * r));
+
+    const int kout = p.kmax - p.kmin + 1;
+    Epi epi;
+    epi.s_edge = p.scale;
+    epi.s_int = 2.0f * p.scale;
+    epi.floor = p.db_floor;
+    epi.kmin = p.kmin;
+    epi.kmax = p.kmax;
+    epi.db = p.out_mode;
+
+    for (long long u = (long long)blockIdx.x * PL::FPC + grp; u < p.n_units; u += (long long)gridDim.x * PL::FPC) {
+        const long long b = u / p.units_per_signal;
+        const int c = (int)(u - b * p.units_per_signal);
+        const int f_begin = c * p.chunk_frames;
+        const int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
+        const Tin* const xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride;
+        float* const ob = p.out + b * p.out_batch_stride - p.kmin;
+
+        for (int f = f_begin; f < f_end; ++f) {
+            const Tin* const xf = xb + (p.frame0 + f) * (long long)p.hop;
+            epi.row = ob + (long long)f * kout;
+
+            // ---- gather: z[n] = x[2n] + i x[2n+1], n = j + G r ----
+            float2 v[16];
+            if (p.vec_ok) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = Loader<Tin>::ld2(xf + 2 * (j + G * r));
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const Tin* q = xf + 2 * (j + G * r);
+                    v[r] = cmk(Loader<Tin>::ld1(q), Loader<Tin>::ld1(q + 1));
+                }
+            }
+
+            // ---- detrend='constant': per-frame mean (scipy _signaltools.py:4288-4290) ----
+            // Two passes in fp32: a coarse mean m1, then the mean r of the residual
+            // x - m1.  The residual is small whatever the DC level of the recording, so
+            // r is accurate relative to the signal's own scale; it is removed inside the
+            // window multiply with a single rounding: (x' - r) w = fma(x', w, -r w).
+            if (p.detrend) {
+                const float m1 = group_mean<LOG2N>(v, gmask, grp, j, lane, red);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { v[r].x -= m1; v[r].y -= m1; }
+                const float nr = -group_mean<LOG2N>(v, gmask, grp, j, lane, red + PL::RED);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    v[r].x = fmaf(v[r].x, win[r].x, nr * win[r].x);
+                    v[r].y = fmaf(v[r].y, win[r].y, nr * win[r].y);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { v[r].x *= win[r].x; v[r].y *= win[r].y; }
+            }
+
+            // ---- pass 0: radix-16 over r (stride G), Ns 1 -> 16 ----
+            radix16(v);
+            group_sync<G>(gmask, grp);          // previous frame's final-stage reads are done
+            {
+                float4* dst = reinterpret_cast<float4*>(buf + 18 * j);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 a = v[perm16(2 * i)], bq = v[perm16(2 * i + 1)];
+                    dst[i] = make_float4(a.x, a.y, bq.x, bq.y);
+                }
+            }
+            group_sync<G>(gmask, grp);
+
+            // ---- passes 1..P-1: radix-16 Stockham, Ns = 16^pass ----
+#pragma unroll
+            for (int pass = 1; pass < PL::P; ++pass) {
+                const int Ns = (pass == 1) ? 16 : 256;
+                const int jm = j & (Ns - 1);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = buf[phys(j + r * G)];
+                const int estep = 2 * jm * (M / (16 * Ns));      // table index step per r
+#pragma unroll
+                for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(p.tw + r * estep));
+                radix16(v);
+                group_sync<G>(gmask, grp);
+                const int base = (j - jm) * 16 + jm;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) buf[phys(base + r * Ns)] = v[perm16(r)];
+                group_sync<G>(gmask, grp);
+            }
+
+            // ---- fused final stage: radix-GF butterflies + real-FFT split + PSD ----
+#pragma unroll
+            for (int cc = 0; cc < PL::TPT; ++cc) {
+                const int kap = j + G * cc;            // task id == kappa in [0, NS/2)
+                float2 U[GF], V[GF];
+                if (kap != 0) {
+                    const int kap2 = NS - kap;
+#pragma unroll
+                    for (int r = 0; r < GF; ++r) {
+                        U[r] = buf[phys(kap + r * NS)];
+                        V[r] = buf[phys(kap2 + r * NS)];
+                    }
+#pragma unroll
+                    for (int r = 1; r < GF; ++r) {
+                        U[r] = cmul(U[r], __ldg(p.tw + 2 * r * kap));
+                        V[r] = cmul(V[r], __ldg(p.tw + 2 * r * kap2));
+                    }
+                    SmallFft<GF>::run(U);
+                    SmallFft<GF>::run(V);
+#pragma unroll
+                    for (int a = 0; a < GF; ++a) {
+                        const int k = kap + a * NS;
+                        epi.pair(k, M - k, U[a], V[GF - 1 - a], __ldg(p.tw + k));
+                    }
+                } else {
+                    // kappa = 0 and kappa = NS/2 are their own mirrors
+#pragma unroll
+                    for (int r = 0; r < GF; ++r) {
+                        U[r] = buf[phys(r * NS)];
+                        V[r] = buf[phys(NS / 2 + r * NS)];
+                    }
+#pragma unroll
+                    for (int r = 1; r < GF; ++r) V[r] = cmul(V[r], __ldg(p.tw + r * NS));
+                    SmallFft<GF>::run(U);
+                    SmallFft<GF>::run(V);
+                    epi.dc_nyq(M, U[0]);
+#pragma unroll
+                    for (int a = 1; 2 * a < GF; ++a)
+                        epi.pair(a * NS, M - a * NS, U[a], U[GF - a], __ldg(p.tw + a * NS));
+                    if constexpr (GF % 2 == 0) epi.self_mid(M / 2, U[GF / 2]);
+#pragma unroll
+                    for (int a = 0; 2 * a < GF - 1; ++a) {
+                        const int k = NS / 2 + a * NS;
+                        epi.pair(k, M - k, V[a], V[GF - 1 - a], __ldg(p.tw + k));
+                    }
+                    if constexpr (GF % 2 == 1) epi.self_mid(NS / 2 + ((GF - 1) / 2) * NS, V[(GF - 1) / 2]);
+                }
+            }
+        }
+    }
+}
+
+// ---- deterministic sum over the batch axis (cross-sweep mean) ----
+// in: [batch][elems] (row stride in_stride), out[slab][elems] partial sums over
+// a slab of rows; a second launch with batch = n_slabs folds the partials.
+B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stride, int batch,
+                                 int rows_per_slab, long long elems, float* __restrict__ out,
+                                 float post_scale) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int slab = (int)blockIdx.y;
+    if (e >= elems) return;
+    const int r0 = slab * rows_per_slab;
+    const int r1 = (r0 + rows_per_slab < batch) ? r0 + rows_per_slab : batch;
+    const float* q = in + (long long)r0 * in_stride + e;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {
+        a0 += q[0];
+        a1 += q[in_stride];
+        a2 += q[2 * in_stride];
+        a3 += q[3 * in_stride];
+        q += 4 * in_stride;
+    }
+    for (; r < r1; ++r) { a0 += q[0]; q += in_stride; }
+    out[(long long)slab * elems + e] = ((a0 + a1) + (a2 + a3)) * post_scale;
+}
+
+}  // namespace b2s

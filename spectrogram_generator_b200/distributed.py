@@ -1,0 +1,136 @@
+"""Sharding the spectrogram path across GPUs (one process per GPU).
+
+The forward STFT has no data dependency between frames, so the path shards
+without any exchange:
+
+  * sweeps / channels  -> contiguous blocks of rows per rank (configs 2, 4);
+  * one long recording -> contiguous *frame* ranges per rank; rank r reads the
+    samples ``[f0*hop, (f0+c-1)*hop + nperseg)`` -- the ``nperseg-hop`` halo it
+    shares with its neighbour is read-only input (config 3).
+
+Two collectives exist, both after the kernels: the all-reduce of the per-rank
+partial *sum* spectrogram for the cross-sweep mean, and the gather of per-rank
+slabs to the exporting rank.  They go through ``torch.distributed`` (NCCL on
+GPUs; gloo in the CPU tests, where the per-rank compute is injected).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .spectrogram import Plan, _to_device, engine, split_frames, triage
+from .windows import rfftfreq, time_axis
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def shard_rows(n_rows: int, world_size: int, rank: int):
+    """Contiguous block ``[lo, hi)`` of rows (sweeps / channels) owned by ``rank``."""
+    base, rem = divmod(n_rows, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_frames(nframes: int, world_size: int, rank: int):
+    """Contiguous frame range ``(f0, count)`` owned by ``rank``."""
+    return split_frames(nframes, world_size)[rank]
+
+
+def sample_span(f0: int, count: int, hop: int, nperseg: int):
+    """Samples ``[lo, hi)`` a rank needs for frames ``[f0, f0+count)`` (halo included)."""
+    if count <= 0:
+        return f0 * hop, f0 * hop
+    return f0 * hop, (f0 + count - 1) * hop + nperseg
+
+
+Compute = Callable[[np.ndarray, Plan], torch.Tensor]
+
+
+def _cuda_compute(x2d: np.ndarray, plan: Plan) -> torch.Tensor:
+    eng = engine()
+    eng.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return eng.stft_psd(_to_device(x2d, dev), plan)
+
+
+def mean_spectrogram_sharded(x_local, total_sweeps: int, fs=1.0, window=("tukey", .25), nperseg=None,
+                             noverlap=None, detrend="constant", scaling="density", *, group=None,
+                             compute: Optional[Compute] = None, return_local=False):
+    """Cross-sweep mean with sweeps sharded over ranks.
+
+    ``x_local[B_r, N]`` holds this rank's sweeps (``shard_rows``).  Each rank sums
+    its own spectrograms on the device, one ``all_reduce(SUM)`` of ``[F, K]`` fp32
+    follows, then the division by ``total_sweeps``.  Returns ``(f, t, Smean[K, F])``
+    as a torch tensor on the compute device (identical on every rank)."""
+    x_local = np.asarray(x_local)
+    plan = triage(x_local.shape[-1], fs, window, nperseg, noverlap, None, detrend, True, scaling, "psd")
+    compute = compute or _cuda_compute
+    S = compute(x_local.reshape(-1, plan.n), plan) if x_local.shape[0] else None
+    if S is None:
+        raise ValueError("every rank needs at least one sweep")
+    if S.is_cuda:
+        part = engine().batch_sum(S, 1.0)
+    else:                                    # injected CPU compute (gloo tests)
+        part = S.sum(dim=0)
+    ws, _ = world(group)
+    if ws > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    mean = part * (1.0 / float(total_sweeps))
+    f = rfftfreq(plan.nperseg, fs)
+    t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+    out = (f, t, mean.transpose(-1, -2))
+    return out + (S,) if return_local else out
+
+
+def spectrogram_time_sharded(x_span, n_total: int, fs=1.0, window=("tukey", .25), nperseg=None,
+                             noverlap=None, detrend="constant", scaling="density", *, group=None,
+                             compute: Optional[Compute] = None):
+    """One long recording, frame ranges sharded over ranks.
+
+    ``x_span`` is this rank's sample slice ``x[lo:hi]`` with ``(lo, hi) =
+    sample_span(*shard_frames(F, world, rank), hop, nperseg)``; ``n_total`` is the
+    length of the whole recording (for the global time axis).  Returns
+    ``(f, t_local, S_local[F_r, K], (f0, count))`` -- ``t_local`` is cut from the
+    global axis so the sharded run equals the unsharded one bit for bit."""
+    plan_g = triage(int(n_total), fs, window, nperseg, noverlap, None, detrend, True, scaling, "psd")
+    ws, rk = world(group)
+    f0, count = shard_frames(plan_g.nframes, ws, rk)
+    lo, hi = sample_span(f0, count, plan_g.hop, plan_g.nperseg)
+    x_span = np.asarray(x_span)
+    if x_span.shape[-1] != hi - lo:
+        raise ValueError(f"rank {rk} expects samples [{lo}, {hi}) of the recording")
+    f = rfftfreq(plan_g.nperseg, fs)
+    t = time_axis(plan_g.n, plan_g.nperseg, plan_g.noverlap, fs)[f0:f0 + count]
+    compute = compute or _cuda_compute
+    if count == 0:
+        return f, t, None, (f0, count)
+    sub = Plan(**{**plan_g.__dict__, "n": hi - lo, "nframes": count})
+    S = compute(x_span.reshape(1, -1), sub)[0]
+    return f, t, S, (f0, count)
+
+
+def gather_slabs(local: torch.Tensor, counts, dst: int = 0, *, group=None):
+    """Gather per-rank slabs ``[rows_r, ...]`` (rows_r = counts[r]) to rank ``dst``
+    and concatenate along dim 0; other ranks return ``None``.  This is the "final
+    gather to the exporting rank"."""
+    ws, rk = world(group)
+    if ws == 1:
+        return local
+    tail = tuple(local.shape[1:])
+    if rk == dst:
+        bufs = [torch.empty((int(c),) + tail, dtype=local.dtype, device=local.device) for c in counts]
+        bufs[rk] = local.contiguous()
+        reqs = [dist.irecv(bufs[r], src=r, group=group) for r in range(ws) if r != dst and counts[r] > 0]
+        for q in reqs:
+            q.wait()
+        return torch.cat(bufs, dim=0)
+    if counts[rk] > 0:
+        dist.send(local.contiguous(), dst=dst, group=group)
+    return None

@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference's ``PlotEngine`` spectrogram path.
+
+``SpectrogramPath`` carries the compute half of the ``PlotEngine`` methods that
+sit on the hot path (/root/reference/PlotEngine.py) with the same names,
+argument meaning and state (``last_f / last_t / last_Sxx``), minus everything
+that draws:
+
+  * ``_plot_spectrogram``      PlotEngine.py:110-131 (call, band mask, display scaling)
+  * ``_calculate_features``    PlotEngine.py:229-242 (band power, log10, first difference)
+  * ``calculate_absolute_power`` / ``calculate_band_powers``   PlotEngine.py:686-719
+  * ``combine``                PlotEngine.py:162-200 (time concatenation + segment map)
+
+The spectrogram itself is computed on the GPU; the band mask
+``(f >= fmin) & (f <= fmax)`` becomes a bin crop inside the kernel's store, so
+only the kept bins are written and copied back.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .spectrogram import _prepare_input, _to_device, _to_host, engine, triage
+from .windows import rfftfreq, time_axis
+
+DEFAULT_BANDS = {
+    # PlotEngine.py:698-706
+    "Delta (δ)": (0, 4), "Theta (θ)": (4, 8),
+    "Alpha (α)": (8, 13), "Beta (β)": (13, 30),
+    "Gamma (γ)": (30, 80), "HFO (ripples)": (80, 250),
+}
+
+
+def band_to_bins(f: np.ndarray, fmin: float, fmax: float):
+    """Bin range selected by the reference's mask ``(f >= fmin) & (f <= fmax)``
+    (PlotEngine.py:114).  ``f`` is increasing, so the mask is a contiguous range;
+    returns ``(kmin, kmax)`` inclusive, or ``None`` when the mask is empty."""
+    idx = np.nonzero((f >= fmin) & (f <= fmax))[0]
+    if idx.size == 0:
+        return None
+    return int(idx[0]), int(idx[-1])
+
+
+class SpectrogramPath:
+    def __init__(self, device=None):
+        self.device = device
+        self.spec_data_source = None
+        self.last_fs = None
+        self.last_settings = None
+        self.last_t = np.array([])
+        self.last_f = None
+        self.last_Sxx = None
+        self.segment_map = []
+
+    # -- the call at PlotEngine.py:113 / :232, with the band mask fused as a crop --
+    def _spectrogram_cropped(self, data, fs, nperseg, fmin, fmax):
+        x, out_dtype, is_complex = _prepare_input(data, -1)
+        if x.ndim != 1:
+            raise ValueError("the reference passes one 1-D sweep per call")
+        plan = triage(x.shape[-1], fs, ("tukey", .25), nperseg, None, None, "constant", True,
+                      "density", "psd", is_complex)
+        f = rfftfreq(plan.nperseg, fs)
+        t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+        bins = band_to_bins(f, fmin, fmax)
+        if bins is None or plan.nframes == 0:
+            return f[:0], t, np.empty((0, plan.nframes), dtype=out_dtype)
+        eng = engine()
+        eng.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None \
+            else torch.device(self.device)
+        with torch.cuda.device(dev):
+            xd = _to_device(x.reshape(1, -1), dev)
+            Sd = eng.stft_psd(xd, plan, kmin=bins[0], kmax=bins[1])
+            S = _to_host(Sd[0], out_dtype)
+        return f[bins[0]:bins[1] + 1], t, S.T
+
+    def _plot_spectrogram(self, data, fs, settings, global_max=None):
+        """PlotEngine.py:110-131.  Returns the normalised image the reference hands
+        to ``pcolormesh`` (``None`` when the band mask is empty)."""
+        nperseg, fmin, fmax, log_scale = (settings["nperseg"], settings["fmin"], settings["fmax"],
+                                          settings["log_scale"])
+        f, t, Sxx = self._spectrogram_cropped(data, fs, nperseg, fmin, fmax)
+        self.last_f = f.copy()
+        self.last_t = t.copy()
+        self.last_Sxx = Sxx.copy()
+        if Sxx.size == 0:
+            self.last_t = np.array([])
+            return None
+        base = np.max(Sxx) if global_max is None or global_max <= 0 else global_max
+        Sxx_norm = np.clip(Sxx / (base + 1e-20), 0.0, 1.0)
+        if log_scale:
+            eps = 1e-12
+            Sxx_db = 10.0 * np.log10(Sxx_norm + eps)
+            Sxx_db = np.nan_to_num(Sxx_db)
+            min_db, max_db = np.min(Sxx_db), np.max(Sxx_db)
+            Sxx_norm = (Sxx_db - min_db) / (max_db - min_db) if (max_db - min_db) > 1e-6 \
+                else np.zeros_like(Sxx_db)
+        return Sxx_norm
+
+    def plot_extra(self, signal_raw, signal_proc, fs, settings, global_max=None):
+        """Source selection of PlotEngine.plot_extra (PlotEngine.py:95-105)."""
+        self.last_fs = fs
+        source = None
+        if settings["mode_proc"] in ["Spectrogram", "Both"] and signal_proc is not None:
+            source = signal_proc
+        elif settings["mode_raw"] in ["Spectrogram", "Both"] and signal_raw is not None:
+            source = signal_raw
+        if source is None:
+            return None
+        self.spec_data_source = source
+        self.last_fs = fs
+        self.last_settings = settings
+        return self._plot_spectrogram(source, fs, settings, global_max)
+
+    def _calculate_features(self, signal, fs=None, settings=None):
+        """PlotEngine.py:229-242."""
+        fs = fs or self.last_fs
+        settings = settings or self.last_settings
+        f, t, Sxx = self._spectrogram_cropped(signal, fs, settings["nperseg"], settings["fmin"],
+                                              settings["fmax"])
+        if t.size == 0:
+            return None, None
+        # an empty band mask gives sum over zero bins == 0 for every frame
+        power_feature = np.sum(Sxx, axis=0) if Sxx.shape[0] else np.zeros(t.shape, dtype=Sxx.dtype)
+        log_power = np.log10(power_feature + 1e-20)
+        delta_log_power = np.diff(log_power, prepend=log_power[0])
+        return t, np.column_stack([log_power, delta_log_power])
+
+    def calculate_absolute_power(self):
+        """PlotEngine.py:686-690."""
+        if self.last_Sxx is None:
+            return None
+        return np.sum(self.last_Sxx)
+
+    def calculate_band_powers(self, bands=None):
+        """PlotEngine.py:692-719."""
+        if self.last_Sxx is None or self.last_f is None:
+            return None
+        Sxx_linear = np.maximum(0, self.last_Sxx)
+        if bands is None:
+            bands = DEFAULT_BANDS
+        total_power = np.sum(Sxx_linear)
+        if total_power < 1e-18:
+            return {name: 0.0 for name in bands}
+        power_dict = {}
+        for name, (low, high) in bands.items():
+            mask = (self.last_f >= low) & (self.last_f < high)
+            band_power = np.sum(Sxx_linear[mask, :])
+            power_dict[name] = np.clip(band_power / total_power, 0.0, None)
+        return power_dict
+
+    def combine(self, sweeps_info, settings):
+        """'Combine all sweeps': time concatenation with a segment map
+        (PlotEngine.py:162-200).  Returns the concatenated signal."""
+        self.segment_map = []
+        offset, parts = 0.0, []
+        use_proc = settings.get("draw_proc", True)
+        for info in sweeps_info:
+            sig_raw = info["signal_raw"]
+            sig_proc = info["signal_proc"] if info["signal_proc"] is not None else info["signal_raw"]
+            sig = sig_proc if use_proc else sig_raw
+            if sig is None:
+                continue
+            duration = len(sig) / info["fs"]
+            self.segment_map.append({"start_time_combined": offset,
+                                     "end_time_combined": offset + duration,
+                                     "source_item": info.get("item")})
+            parts.append(sig)
+            offset += duration
+        return np.concatenate(parts) if parts else None

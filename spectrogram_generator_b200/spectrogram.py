@@ -1,0 +1,384 @@
+"""Host side of the spectrogram path: SciPy's call surface over the CUDA library.
+
+``spectrogram`` mirrors ``scipy.signal.spectrogram`` (the function the
+reference imports at PlotEngine.py:8 and calls at :113 / :232): same signature,
+defaults, validation messages, warnings and return layout -- ``(f, t, Sxx)``
+NumPy arrays with ``Sxx`` a transposed view of a C-contiguous
+``[..., frame, bin]`` buffer, exactly what SciPy hands back.  The arithmetic runs
+in ``libb200stft.so`` (fp32, sm_100a); PyTorch is used for device memory,
+streams and pinned staging only.  Unsupported keyword combinations raise --
+there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import threading
+import warnings
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .windows import frame_count, get_window, rfftfreq, time_axis
+
+_MODES = ["psd", "complex", "magnitude", "angle", "phase"]
+
+
+# --------------------------------------------------------------------------
+# argument triage (scipy/signal/_spectral_py.py:1119-1129, 2209-2230, 2400-2461)
+# --------------------------------------------------------------------------
+
+@dataclass
+class Plan:
+    """Everything the kernel launch and the axis arrays need for one call."""
+    n: int                 # samples along the time axis
+    nperseg: int
+    noverlap: int
+    hop: int
+    fs: float
+    win64: np.ndarray      # float64 window (host)
+    scale: float           # 1/(fs*sum(w^2)) or 1/sum(w)^2, float64
+    detrend: int           # 0 / 1
+    nframes: int
+    nbins: int
+    window_key: tuple
+
+
+def _window_key(window, nperseg):
+    if isinstance(window, (str, tuple)):
+        return ("spec", window, int(nperseg))
+    a = np.ascontiguousarray(np.asarray(window, dtype=np.float64))
+    return ("array", a.tobytes(), int(nperseg))
+
+
+def triage(n, fs, window, nperseg, noverlap, nfft, detrend, return_onesided, scaling, mode,
+           is_complex=False) -> Plan:
+    """Validate like SciPy does and derive the launch plan.  Raises the same
+    ``ValueError``s (and the ``nperseg > len(x)`` ``UserWarning``); combinations
+    the engine does not implement raise ``NotImplementedError``."""
+    if mode not in _MODES:
+        raise ValueError(f"unknown value for mode {mode}, must be one of {_MODES}")
+    if mode != "psd":
+        raise NotImplementedError(f"mode={mode!r}: the B200 engine implements mode='psd' "
+                                  "(the reference's only mode, PlotEngine.py:113)")
+    if is_complex:
+        raise NotImplementedError("complex input is not on the reference's path")
+    if not return_onesided:
+        raise NotImplementedError("return_onesided=False is not implemented (real input only)")
+    # spectrogram() runs _triage_segments first (:1124), so a non-positive or
+    # non-integral nperseg surfaces as get_window's ValueError, as in SciPy
+    if isinstance(window, (str, tuple)):
+        if nperseg is None:
+            nperseg = 256
+        if nperseg > n:
+            warnings.warn(f"nperseg = {nperseg:d} is greater than input length "
+                          f" = {n:d}, using nperseg = {n:d}", stacklevel=4)
+            nperseg = n
+        win = get_window(window, nperseg)          # raises ValueError for nperseg == 0 like SciPy
+    else:
+        win = np.asarray(window)
+        if win.ndim != 1:
+            raise ValueError("window must be 1-D")
+        if n < win.shape[-1]:
+            raise ValueError("window is longer than input signal")
+        if nperseg is None:
+            nperseg = win.shape[0]
+        elif nperseg != win.shape[0]:
+            raise ValueError("value specified for nperseg is different from length of window")
+        win = np.asarray(win, dtype=np.float64)
+    nperseg = int(nperseg)
+    if nperseg < 1:                                  # _spectral_helper, :2209-2212
+        raise ValueError("nperseg must be a positive integer")
+    if nfft is None:
+        nfft = nperseg
+    elif nfft < nperseg:
+        raise ValueError("nfft must be greater than or equal to nperseg.")
+    elif int(nfft) != nperseg:
+        raise NotImplementedError("nfft != nperseg (zero-padded FFT) is not implemented")
+    if noverlap is None:
+        noverlap = nperseg // 8                      # spectrogram's default, :1128-1129
+    else:
+        noverlap = int(noverlap)
+    if noverlap >= nperseg:
+        raise ValueError("noverlap must be less than nperseg.")
+    if not detrend:
+        det = 0
+    elif detrend == "constant":
+        det = 1
+    else:
+        raise NotImplementedError(f"detrend={detrend!r}: only 'constant' (the reference's) and False")
+    if scaling == "density":
+        scale = 1.0 / (fs * (win * win).sum())
+    elif scaling == "spectrum":
+        scale = 1.0 / win.sum() ** 2
+    else:
+        raise ValueError(f"Unknown scaling: {scaling!r}")
+    hop = nperseg - noverlap
+    return Plan(n=n, nperseg=nperseg, noverlap=noverlap, hop=hop, fs=fs, win64=win, scale=float(scale),
+                detrend=det, nframes=frame_count(n, nperseg, hop), nbins=nperseg // 2 + 1,
+                window_key=_window_key(window, nperseg))
+
+
+# --------------------------------------------------------------------------
+# device engine
+# --------------------------------------------------------------------------
+
+class Engine:
+    """Per-process state: the loaded library and per-device window tables."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._windows = {}
+
+    @staticmethod
+    def require_cuda():
+        if not torch.cuda.is_available():
+            raise _lib.B2SError("no CUDA device: the spectrogram engine has no CPU fallback")
+
+    def window_table(self, plan: Plan, device: torch.device) -> torch.Tensor:
+        key = (plan.window_key, device.index)
+        with self._lock:
+            t = self._windows.get(key)
+            if t is None:
+                if len(self._windows) > 64:
+                    self._windows.clear()
+                t = torch.from_numpy(plan.win64.astype(np.float32)).to(device)
+                self._windows[key] = t
+            return t
+
+    def stft_psd(self, x: torch.Tensor, plan: Plan, *, out=None, out_mode=0, db_floor=0.0,
+                 kmin=0, kmax=None, frame0=0, nframes=None) -> torch.Tensor:
+        """x: CUDA tensor [B, n] (float32 or float64, last dim contiguous).
+        Returns CUDA float32 [B, nframes, kmax-kmin+1].  Enqueued on the current stream."""
+        lib = _lib.load()
+        if x.dim() != 2 or not x.is_cuda:
+            raise ValueError("stft_psd expects a CUDA tensor of shape [batch, n]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        if x.dtype not in (torch.float32, torch.float64):
+            raise TypeError("stft_psd expects float32 or float64 samples")
+        B, n = x.shape
+        if n != plan.n:
+            raise ValueError("plan was made for a different signal length")
+        kmax = plan.nbins - 1 if kmax is None else int(kmax)
+        nframes = plan.nframes - frame0 if nframes is None else int(nframes)
+        kout = kmax - kmin + 1
+        if out is None:
+            out = torch.empty((B, nframes, kout), dtype=torch.float32, device=x.device)
+        elif out.shape != (B, nframes, kout) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 [B, nframes, nbins] tensor")
+        if B == 0 or nframes == 0:
+            return out
+        support = lib.b2s_nperseg_support(plan.nperseg)
+        if support == 0:
+            raise NotImplementedError(
+                f"nperseg={plan.nperseg} is not supported by the B200 engine "
+                "(power-of-two 32..16384 on the fused kernel)")
+        win = self.window_table(plan, x.device)
+        fn = lib.b2s_stft_psd_f32 if x.dtype == torch.float32 else lib.b2s_stft_psd_f64
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop,
+                    win.data_ptr(), plan.detrend, plan.scale, int(out_mode), float(db_floor),
+                    int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
+                    nframes * kout, stream)
+        _lib.check(rc, "b2s_stft_psd")
+        return out
+
+    def batch_sum(self, s: torch.Tensor, post_scale: float = 1.0) -> torch.Tensor:
+        """Deterministic sum over dim 0 of a contiguous CUDA float32 [B, ...] tensor."""
+        lib = _lib.load()
+        if not s.is_cuda or s.dtype != torch.float32 or not s.is_contiguous() or s.dim() < 2:
+            raise ValueError("batch_sum expects a contiguous CUDA float32 tensor [B, ...]")
+        B = s.shape[0]
+        elems = s[0].numel()
+        out = torch.empty(s.shape[1:], dtype=torch.float32, device=s.device)
+        ns = lib.b2s_batch_sum_scratch_elems(B, elems)
+        scratch = torch.empty(ns, dtype=torch.float32, device=s.device) if ns else None
+        with torch.cuda.device(s.device):
+            rc = lib.b2s_batch_sum_f32(s.data_ptr(), B, elems, elems, out.data_ptr(),
+                                       scratch.data_ptr() if scratch is not None else None,
+                                       float(post_scale), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_batch_sum_f32")
+        return out
+
+
+_ENGINE = Engine()
+
+
+def engine() -> Engine:
+    return _ENGINE
+
+
+# --------------------------------------------------------------------------
+# host staging helpers
+# --------------------------------------------------------------------------
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A NumPy array backed by page-locked memory.  Signals placed in such an
+    array are copied to the GPU asynchronously at full PCIe rate."""
+    t = torch.empty(tuple(shape), dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype, pin_memory=True)
+    return t.numpy()
+
+
+def _as_host_tensor(a: np.ndarray) -> torch.Tensor:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # read-only arrays: we never write through it
+        return torch.from_numpy(a)
+
+
+def _result_dtype(x: np.ndarray):
+    """SciPy's rule: Sxx has the real dtype of result_type(x, complex64) (_spectral_py.py:2169)."""
+    return np.float64 if np.result_type(x.dtype, np.complex64) == np.complex128 else np.float32
+
+
+def _prepare_input(x, axis):
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        return x, None, True
+    out_dtype = _result_dtype(x)
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(out_dtype)
+    if x.ndim == 0:
+        raise ValueError("input must be at least 1-D")
+    axis = int(axis)
+    if axis != -1 and axis != x.ndim - 1:
+        x = np.moveaxis(x, axis, -1)
+    return x, out_dtype, False
+
+
+def _to_device(x2d: np.ndarray, device) -> torch.Tensor:
+    if not x2d.flags.c_contiguous:
+        x2d = np.ascontiguousarray(x2d)
+    h = _as_host_tensor(x2d)
+    return h.to(device, non_blocking=h.is_pinned())
+
+
+def _to_host(d: torch.Tensor, dtype) -> np.ndarray:
+    h = torch.empty(d.shape, dtype=d.dtype, pin_memory=True)
+    h.copy_(d, non_blocking=True)
+    torch.cuda.current_stream(d.device).synchronize()
+    a = h.numpy()
+    return a if a.dtype == dtype else a.astype(dtype)
+
+
+# --------------------------------------------------------------------------
+# public API
+# --------------------------------------------------------------------------
+
+def spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=None, nfft=None,
+                detrend="constant", return_onesided=True, scaling="density", axis=-1, mode="psd",
+                *, device=None):
+    """Drop-in for ``scipy.signal.spectrogram`` on the path the reference uses.
+
+    Returns ``(f, t, Sxx)``: ``f`` float64 ``(nperseg//2+1,)``, ``t`` float64
+    ``(n_frames,)`` (both bit-identical to SciPy's), ``Sxx`` of shape
+    ``(..., n_bins, n_frames)`` with SciPy's dtype rule (float32 for
+    float32/int16 input, float64 for float64 input -- the arithmetic is fp32 in
+    both cases).
+    """
+    x, out_dtype, is_complex = _prepare_input(x, axis)
+    plan = triage(x.shape[-1], fs, window, nperseg, noverlap, nfft, detrend, return_onesided,
+                  scaling, mode, is_complex)
+    f = rfftfreq(plan.nperseg, fs)
+    t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+    lead = x.shape[:-1]
+    B = int(np.prod(lead)) if lead else 1
+    eng = engine()
+    eng.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if B == 0 or plan.nframes == 0:
+        S = np.empty(lead + (plan.nframes, plan.nbins), dtype=out_dtype)
+    else:
+        xd = _to_device(x.reshape(B, plan.n), dev)
+        with torch.cuda.device(dev):
+            Sd = eng.stft_psd(xd, plan)
+            S = _to_host(Sd, out_dtype).reshape(lead + (plan.nframes, plan.nbins))
+    # SciPy rolls the frequency axis back to where the data axis was and leaves
+    # the segment-time axis last (:2334-2341); for axis=-1 that is the
+    # [..., bin, frame] transposed view of the [..., frame, bin] buffer.
+    ax = int(axis)
+    if ax < 0:
+        ax -= 1
+    return f, t, np.moveaxis(S, -1, ax)
+
+
+def spectrogram_batch(x, fs=1.0, **kw):
+    """Per-sweep spectrograms of a batch ``x[B, N]`` -> ``(f, t, Sxx[B, K, F])``
+    (same as ``spectrogram`` on a 2-D array; named for BASELINE config 2)."""
+    x = np.asarray(x)
+    if x.ndim != 2:
+        raise ValueError("spectrogram_batch expects x of shape [B, N]")
+    return spectrogram(x, fs=fs, **kw)
+
+
+def mean_spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=None, nfft=None,
+                     detrend="constant", return_onesided=True, scaling="density", mode="psd",
+                     *, return_per_sweep=False, device=None):
+    """Cross-sweep mean spectrogram of ``x[B, N]``: ``mean_b Sxx_b`` (BASELINE
+    config 2; the reference has no code for it -- SURVEY.md 8 a-15).  The sum
+    over sweeps runs on the device in a fixed order.  Returns ``(f, t, Smean[K, F])``
+    or, with ``return_per_sweep``, ``(f, t, Smean, Sxx[B, K, F])``."""
+    x, out_dtype, is_complex = _prepare_input(x, -1)
+    if x.ndim != 2:
+        raise ValueError("mean_spectrogram expects x of shape [B, N]")
+    plan = triage(x.shape[-1], fs, window, nperseg, noverlap, nfft, detrend, return_onesided,
+                  scaling, mode, is_complex)
+    if x.shape[0] == 0 or plan.nframes == 0:
+        raise ValueError("mean_spectrogram needs at least one sweep and one frame")
+    f = rfftfreq(plan.nperseg, fs)
+    t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+    eng = engine()
+    eng.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        xd = _to_device(x, dev)
+        Sd = eng.stft_psd(xd, plan)
+        Md = eng.batch_sum(Sd, 1.0 / x.shape[0])
+        mean = np.moveaxis(_to_host(Md, out_dtype), -1, -2)
+        if return_per_sweep:
+            return f, t, mean, np.moveaxis(_to_host(Sd, out_dtype), -1, -2)
+    return f, t, mean
+
+
+def split_frames(nframes: int, parts: int):
+    """Contiguous frame ranges ``[(f0, count), ...]`` for ``parts`` chunks / ranks."""
+    parts = max(1, int(parts))
+    base, rem = divmod(nframes, parts)
+    out, f0 = [], 0
+    for r in range(parts):
+        c = base + (1 if r < rem else 0)
+        out.append((f0, c))
+        f0 += c
+    return out
+
+
+def spectrogram_chunked(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=None, nfft=None,
+                        detrend="constant", return_onesided=True, scaling="density", mode="psd",
+                        *, n_chunks=8, device=None):
+    """Time-chunked spectrogram of one long 1-D recording (BASELINE config 3 on
+    one GPU): the frame range is cut into ``n_chunks`` contiguous ranges; chunk r
+    is given only its own samples ``[f0*hop, (f0+c-1)*hop + nperseg)`` -- the
+    ``nperseg - hop`` halo it shares with its neighbour is read-only input, so no
+    exchange is needed -- and the results are concatenated.  Bit-identical to the
+    unchunked call (the per-frame arithmetic does not depend on the chunking)."""
+    x, out_dtype, is_complex = _prepare_input(x, -1)
+    if x.ndim != 1:
+        raise ValueError("spectrogram_chunked expects a 1-D recording")
+    plan = triage(x.shape[-1], fs, window, nperseg, noverlap, nfft, detrend, return_onesided,
+                  scaling, mode, is_complex)
+    f = rfftfreq(plan.nperseg, fs)
+    t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+    eng = engine()
+    eng.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    S = np.empty((plan.nframes, plan.nbins), dtype=out_dtype)
+    with torch.cuda.device(dev):
+        for f0, c in split_frames(plan.nframes, n_chunks):
+            if c == 0:
+                continue
+            lo, hi = f0 * plan.hop, (f0 + c - 1) * plan.hop + plan.nperseg
+            sub = Plan(**{**plan.__dict__, "n": hi - lo, "nframes": c})
+            xd = _to_device(x[lo:hi].reshape(1, -1), dev)
+            S[f0:f0 + c] = _to_host(eng.stft_psd(xd, sub)[0], out_dtype)
+    return f, t, S.T

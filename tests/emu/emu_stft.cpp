@@ -1,0 +1,66 @@
+// CPU SIMT-emulator harness for csrc/b2s_kernels.cuh -- TEST TOOLING ONLY.
+// Build: g++ -std=c++20 -O1 -DB2S_EMU -shared -fPIC -pthread -I tests/emu \
+//        -I spectrogram_generator_b200/csrc tests/emu/emu_stft.cpp -o tests/emu/libb2s_emu.so
+#include "emu_cuda.hpp"
+
+thread_local uint3_ threadIdx;
+thread_local uint3_ blockIdx;
+dim3_ blockDim;
+dim3_ gridDim;
+namespace emu { Cta* g_cta = nullptr; }
+
+#include "b2s_host.hpp"
+
+using namespace b2s;
+
+template <int LOG2N>
+static void run_one(const StftArgs& a, StftParams p, unsigned grid) {
+    using PL = Plan<LOG2N>;
+    if (a.x_is_f64)
+        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1>(p); });
+    else
+        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1>(p); });
+}
+
+extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long long n, long long x_batch_stride,
+                            int nperseg, int hop, const float* window, int detrend, double scale, int out_mode,
+                            float db_floor, int kmin, int kmax, long long frame0, long long nframes, float* out,
+                            long long out_batch_stride, int grid, int force_chunk) {
+    StftArgs a{x, x_is_f64, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
+               db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride};
+    StftParams p{};
+    std::string err;
+    const int log2n = plan_stft(a, 1, (long long)grid * 4, p, err);
+    if (log2n < 0) return log2n;
+    if (force_chunk > 0) {
+        p.chunk_frames = force_chunk;
+        p.units_per_signal = (nframes + force_chunk - 1) / force_chunk;
+        p.n_units = p.units_per_signal * batch;
+    }
+    std::vector<float> tw;
+    make_twiddles(nperseg, tw);
+    p.tw = reinterpret_cast<const float2*>(tw.data());
+    if (p.n_units == 0) return 0;
+#define RUN(L) run_one<L>(a, p, (unsigned)grid)
+    B2S_DISPATCH_LOG2N(log2n, RUN)
+#undef RUN
+    return 0;
+}
+
+extern "C" int emu_batch_sum(const float* in, long long in_stride, int batch, int rows_per_slab, long long elems,
+                             float* out, float post_scale) {
+    const unsigned block = 64;
+    const unsigned gx = (unsigned)((elems + block - 1) / block);
+    const unsigned slabs = (unsigned)((batch + rows_per_slab - 1) / rows_per_slab);
+    for (unsigned s = 0; s < slabs; ++s) {
+        // blockIdx.y is not modelled by the emulator: fold it by offsetting pointers
+        emu::launch(gx, block, 0, [&] {
+            blockIdx.y = 0;
+            const int r0 = (int)s * rows_per_slab;
+            const int nb = (batch - r0 < rows_per_slab) ? batch - r0 : rows_per_slab;
+            batch_sum_kernel(in + (long long)r0 * in_stride, in_stride, nb, rows_per_slab, elems,
+                             out + (long long)s * elems, post_scale);
+        });
+    }
+    return 0;
+}

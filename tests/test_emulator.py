@@ -1,0 +1,150 @@
+"""The kernel source itself (csrc/b2s_kernels.cuh), compiled for the CPU SIMT
+emulator (tests/emu) and driven through the library's own launch planning,
+compared against the oracle.  This exercises the index math, shuffles, barrier
+discipline, bin crop, frame ranges and the unaligned load path in the no-GPU
+container; the GPU tests repeat the comparison on the real device."""
+import numpy as np
+import pytest
+
+import spectrogram_generator_b200 as sg
+from oracle import stft_oracle
+from util import assert_parity, load_golden
+
+
+def plan_for(n, fs, **kw):
+    a = dict(window=("tukey", .25), nperseg=None, noverlap=None, nfft=None, detrend="constant",
+             return_onesided=True, scaling="density", mode="psd")
+    a.update(kw)
+    return sg.triage(n, fs, a["window"], a["nperseg"], a["noverlap"], a["nfft"], a["detrend"],
+                     a["return_onesided"], a["scaling"], a["mode"])
+
+
+def signal(B, n, seed, dc=0.25):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    x = 0.3 * rng.standard_normal((B, n)) + np.sin(2 * np.pi * 0.0371 * t) + 0.5 * np.sin(2 * np.pi * 0.21 * t + 1.0) + dc
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("nperseg", [32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_all_sizes_reference_default_overlap(emu, nperseg):
+    """SciPy defaults as the reference uses them: Tukey(.25), noverlap = nperseg//8, detrend."""
+    n = nperseg * 4 + 13
+    x = signal(2, n, nperseg)
+    plan = plan_for(n, 1000.0, nperseg=nperseg)
+    got = emu.stft_psd(x, plan, chunk=2)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=1000.0, nperseg=nperseg)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"nperseg={nperseg}")
+
+
+@pytest.mark.parametrize("nperseg,hop", [(512, 128), (512, 256), (512, 64), (1024, 256), (256, 37),
+                                         (256, 1), (64, 64), (2048, 512), (1024, 333)])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_hops_and_detrend(emu, nperseg, hop, detrend):
+    n = nperseg + hop * 9 + 5
+    x = signal(3, n, hop, dc=2.0 if detrend else 0.0)
+    kw = dict(window="hann", nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = plan_for(n, 20000.0, **kw)
+    got = emu.stft_psd(x, plan)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=str(kw))
+
+
+def test_float64_samples_and_spectrum_scaling(emu):
+    n = 5000
+    x = signal(2, n, 7).astype(np.float64)       # fp32-representable values held as float64
+    kw = dict(window="blackman", nperseg=512, noverlap=100, scaling="spectrum")
+    plan = plan_for(n, 48000.0, **kw)
+    got = emu.stft_psd(x, plan)
+    _, _, So = stft_oracle.spectrogram(x, fs=48000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So)
+
+
+def test_unaligned_base_and_odd_stride_take_the_scalar_path(emu):
+    n = 3001
+    big = signal(1, 2 * n + 8, 11)[0]
+    x = np.stack([big[1:1 + n], big[n + 2:2 * n + 2]])         # odd offsets -> 4-byte aligned only
+    xs = np.lib.stride_tricks.as_strided(big[1:], shape=(2, n), strides=((n + 1) * 4, 4))
+    assert np.array_equal(x, xs)
+    kw = dict(window="hann", nperseg=256, noverlap=192)
+    plan = plan_for(n, 1.0, **kw)
+    got = emu.stft_psd(np.ascontiguousarray(xs), plan)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=1.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So)
+
+
+def test_bin_crop_frame_range_and_db(emu):
+    n = 9000
+    x = signal(2, n, 5)
+    kw = dict(window="hann", nperseg=1024, noverlap=768)
+    plan = plan_for(n, 8000.0, **kw)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=8000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    full = emu.stft_psd(x, plan)
+    part = emu.stft_psd(x, plan, kmin=17, kmax=300, frame0=5, nframes=11)
+    assert np.array_equal(part, full[:, 5:16, 17:301])          # crop/range do not change the arithmetic
+    floor = 1e-6 * So.max()
+    db = emu.stft_psd(x, plan, out_mode=1, db_floor=floor)
+    want = stft_oracle.to_db(So, floor)
+    big = So >= floor
+    assert np.max(np.abs(db[big] - want[big])) <= 1e-3
+    assert np.all(db >= 10 * np.log10(floor) - 1e-3)
+
+
+def test_chunking_is_bit_identical(emu):
+    n = 20000
+    x = signal(1, n, 3)
+    kw = dict(window="hann", nperseg=512, noverlap=384)
+    plan = plan_for(n, 1.0, **kw)
+    a = emu.stft_psd(x, plan, chunk=1, grid=1)
+    b = emu.stft_psd(x, plan, chunk=7, grid=3)
+    assert np.array_equal(a, b)
+    # time-chunking with a halo: each chunk sees only its own samples
+    pieces = []
+    for f0, c in sg.split_frames(plan.nframes, 4):
+        lo, hi = f0 * plan.hop, (f0 + c - 1) * plan.hop + plan.nperseg
+        sub = plan_for(hi - lo, 1.0, **kw)
+        pieces.append(emu.stft_psd(x[:, lo:hi], sub))
+    assert np.array_equal(np.concatenate(pieces, axis=1), a)
+
+
+@pytest.mark.parametrize("name", ["ref_call_256", "ref_call_1024", "c1_chirp_025s", "c2_sweeps_4x02s", "clamp_64"])
+def test_golden_fixtures(emu, name):
+    import warnings
+    g = load_golden(name)
+    x = np.atleast_2d(g["x"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = plan_for(x.shape[-1], g["fs"], **g["kw"])
+    got = np.moveaxis(emu.stft_psd(x, plan), -1, -2)
+    assert_parity(got.reshape(g["Sxx"].shape), g["Sxx"], what=name)
+    if "mean" in g:
+        m = emu.batch_sum(np.moveaxis(got, -1, -2), 1.0 / x.shape[0]).T
+        assert np.max(np.abs(m - g["mean"])) <= 1e-6 * g["mean"].max()
+
+
+def test_batch_sum_is_deterministic_and_slabbed(emu):
+    rng = np.random.default_rng(0)
+    s = rng.random((200, 7, 33)).astype(np.float32)
+    a = emu.batch_sum(s, 1.0 / 200)
+    b = emu.batch_sum(s, 1.0 / 200)
+    assert np.array_equal(a, b)
+    np.testing.assert_allclose(a, s.astype(np.float64).mean(axis=0), rtol=2e-6)
+
+
+def test_parseval_and_linearity(emu):
+    """Size-independent properties: with detrend=False the one-sided density
+    integrates to the windowed frame energy; the power scales with amplitude^2."""
+    n = 6000
+    x = signal(1, n, 9, dc=0.0)
+    kw = dict(window="hann", nperseg=256, noverlap=128, detrend=False)
+    fs = 1234.0
+    plan = plan_for(n, fs, **kw)
+    S = emu.stft_psd(x, plan)[0].astype(np.float64)                     # [F, K]
+    w = plan.win64
+    frames = np.lib.stride_tricks.sliding_window_view(x[0].astype(np.float64), 256)[::128]
+    energy = ((frames * w) ** 2).sum(axis=1)
+    lhs = S.sum(axis=1) * fs / 256 * (w * w).sum()
+    np.testing.assert_allclose(lhs, energy, rtol=2e-6)
+    S4 = emu.stft_psd(2.0 * x, plan)[0]
+    np.testing.assert_array_equal(S4, 4.0 * emu.stft_psd(x, plan)[0])   # exact: power-of-two scaling

@@ -1,0 +1,101 @@
+"""Shared test helpers: tolerances, golden loading, the emulator wrapper."""
+from __future__ import annotations
+
+import ast
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+
+# ---- tolerances (BASELINE.md section 5 / SURVEY.md 8c) -------------------------------
+REL_TOL = 1e-4          # linear power, relative, on bins >= FLOOR * max(S)
+FLOOR = 1e-6            # peak - 60 dB
+ABS_TOL = 1e-6          # |dS| <= ABS_TOL * max(S) everywhere
+DB_TOL = 1e-3           # dB above the floor
+
+
+def parity_report(S, So, floor=FLOOR):
+    """S: engine result (fp32 arithmetic), So: float64 oracle, same shape."""
+    S = np.asarray(S, dtype=np.float64)
+    So = np.asarray(So, dtype=np.float64)
+    assert S.shape == So.shape, (S.shape, So.shape)
+    peak = So.max() if So.size else 0.0
+    big = So >= floor * peak
+    d = np.abs(S - So)
+    rel = float((d[big] / So[big]).max()) if big.any() else 0.0
+    db = float(np.abs(10 * np.log10(np.maximum(S[big], 1e-300)) - 10 * np.log10(So[big])).max()) if big.any() else 0.0
+    return dict(rel=rel, abs=float(d.max() / peak) if peak > 0 else float(d.max()), db=db,
+                finite=bool(np.isfinite(S).all()))
+
+
+def assert_parity(S, So, rel=REL_TOL, floor=FLOOR, abs_tol=ABS_TOL, db=DB_TOL, what=""):
+    r = parity_report(S, So, floor)
+    assert r["finite"], f"{what}: non-finite values"
+    assert r["rel"] <= rel, f"{what}: rel err {r['rel']:.3e} > {rel} above the {floor:g}*max floor"
+    assert r["abs"] <= abs_tol, f"{what}: abs err {r['abs']:.3e} * max > {abs_tol}"
+    assert r["db"] <= db, f"{what}: dB err {r['db']:.3e} > {db}"
+    return r
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    d["kw"] = ast.literal_eval(str(d["kw"]))
+    d["fs"] = float(d["fs"])
+    return d
+
+
+GOLDEN_NAMES = ["ref_call_256", "ref_call_1024", "c1_chirp_025s", "c2_sweeps_4x02s", "int16_512", "clamp_64"]
+
+
+class Emulator:
+    """Runs csrc/b2s_kernels.cuh on the CPU (tests/emu) through the same launch
+    planning code as the CUDA library.  Test tooling only."""
+
+    def __init__(self):
+        import __graft_entry__ as ge
+        self.lib = ctypes.CDLL(ge.build_emulator())
+        c = ctypes
+        self.lib.emu_stft_psd.restype = c.c_int
+        self.lib.emu_stft_psd.argtypes = [c.c_void_p, c.c_int, c.c_longlong, c.c_longlong, c.c_longlong,
+                                          c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_double, c.c_int,
+                                          c.c_float, c.c_int, c.c_int, c.c_longlong, c.c_longlong,
+                                          c.c_void_p, c.c_longlong, c.c_int, c.c_int]
+        self.lib.emu_batch_sum.restype = c.c_int
+        self.lib.emu_batch_sum.argtypes = [c.c_void_p, c.c_longlong, c.c_int, c.c_int, c.c_longlong,
+                                           c.c_void_p, c.c_float]
+
+    def stft_psd(self, x2d, plan, out_mode=0, db_floor=0.0, kmin=0, kmax=None, frame0=0, nframes=None,
+                 grid=2, chunk=0):
+        x2d = np.ascontiguousarray(x2d)
+        assert x2d.dtype in (np.float32, np.float64) and x2d.ndim == 2
+        B, n = x2d.shape
+        kmax = plan.nbins - 1 if kmax is None else kmax
+        nframes = plan.nframes - frame0 if nframes is None else nframes
+        kout = kmax - kmin + 1
+        w = plan.win64.astype(np.float32)
+        out = np.full((B, nframes, kout), np.nan, np.float32)
+        rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
+                                   plan.hop, w.ctypes.data, plan.detrend, plan.scale, out_mode, db_floor,
+                                   kmin, kmax, frame0, nframes, out.ctypes.data, nframes * kout, grid, chunk)
+        assert rc == 0, rc
+        return out
+
+    def batch_sum(self, s, post_scale=1.0, rows_per_slab=64):
+        s = np.ascontiguousarray(s, dtype=np.float32)
+        B = s.shape[0]
+        elems = s[0].size
+        slabs = (B + rows_per_slab - 1) // rows_per_slab
+        if slabs == 1:
+            out = np.empty(s.shape[1:], np.float32)
+            self.lib.emu_batch_sum(s.ctypes.data, elems, B, B, elems, out.ctypes.data, post_scale)
+            return out
+        part = np.empty((slabs,) + s.shape[1:], np.float32)
+        self.lib.emu_batch_sum(s.ctypes.data, elems, B, rows_per_slab, elems, part.ctypes.data, 1.0)
+        out = np.empty(s.shape[1:], np.float32)
+        self.lib.emu_batch_sum(part.ctypes.data, elems, slabs, slabs, elems, out.ctypes.data, post_scale)
+        return out
