@@ -55,8 +55,9 @@ def _worker(args):
     f, t, S = reference_call_kw(x, fs, **kw)
     if want_db:
         S = 10.0 * np.log10(np.maximum(S, floor_rel * S.max()))
-    # reduce to something small so inter-process transfer does not dominate
-    return S.shape, float(S.sum())
+    # each worker returns its partial sum over sweeps (the cross-sweep mean's numerator);
+    # the per-sweep spectrograms stay in the worker, as they would stay on a GPU
+    return S.shape, S.reshape((-1,) + S.shape[-2:]).sum(axis=0)
 
 
 def run_sharded(x2d, fs, kw, n_procs, want_db=False, floor_rel=1e-6):

@@ -1,0 +1,80 @@
+"""Drop-in check: the reference's PlotEngine post-processing (restated from
+PlotEngine.py:110-131, :229-242, :686-719 in oracle/) run once over SciPy's result
+and once over the engine's, with the same settings dict the GUI builds
+(GUI.py:421-431)."""
+import numpy as np
+import pytest
+
+import spectrogram_generator_b200 as sg
+from oracle import reference_path, stft_oracle
+from util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def sweep(n=40000, fs=20000.0, seed=0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    burst = (np.sin(2 * np.pi * 18.0 * t) * (np.abs(t - 1.0) < 0.3)).astype(np.float64)
+    return (0.05 * rng.standard_normal(n) + 0.4 * np.sin(2 * np.pi * 7.0 * t) + burst - 0.065).astype(np.float32), fs
+
+
+@pytest.mark.parametrize("settings", [
+    dict(nperseg=1024, fmin=0.0, fmax=30.0, log_scale=False),       # GUI defaults (GUI.py:218-221)
+    dict(nperseg=1024, fmin=0.0, fmax=30.0, log_scale=True),
+    dict(nperseg=4096, fmin=1.0, fmax=250.0, log_scale=True),
+    dict(nperseg=256, fmin=100.0, fmax=5000.0, log_scale=False),
+])
+def test_plot_spectrogram_matches_reference_postprocessing(settings):
+    x, fs = sweep()
+    ref = reference_path.plot_spectrogram_compute(x.astype(np.float64), fs, settings)
+    path = sg.SpectrogramPath()
+    img = path._plot_spectrogram(x, fs, settings)
+    assert np.array_equal(path.last_f, ref["last_f"]) and np.array_equal(path.last_t, ref["last_t"])
+    assert_parity(path.last_Sxx, ref["last_Sxx"], what="last_Sxx")
+    assert img.shape == ref["image"].shape
+    if settings["log_scale"]:
+        # min-max normalised dB image over a ~120 dB range: 1e-3 dB <-> ~1e-5 of full scale
+        assert np.max(np.abs(img - ref["image"])[ref["last_Sxx"] >= 1e-6 * ref["last_Sxx"].max()]) <= 2e-5
+    else:
+        assert np.max(np.abs(img - ref["image"])) <= 1e-4
+    np.testing.assert_allclose(path.calculate_absolute_power(), stft_oracle.absolute_power(ref["last_Sxx"]), rtol=1e-5)
+    bp, bpr = path.calculate_band_powers(), stft_oracle.band_powers(ref["last_f"], ref["last_Sxx"])
+    for k in bpr:
+        assert abs(bp[k] - bpr[k]) <= 1e-5
+
+
+def test_empty_band_mask_follows_reference_early_return():
+    x, fs = sweep()
+    path = sg.SpectrogramPath()
+    assert path._plot_spectrogram(x, fs, dict(nperseg=1024, fmin=1e6, fmax=2e6, log_scale=False)) is None
+    assert path.last_t.size == 0 and path.last_Sxx.size == 0
+
+
+def test_calculate_features_matches_reference():
+    x, fs = sweep(seed=2)
+    settings = dict(nperseg=1024, fmin=0.0, fmax=30.0, log_scale=False)
+    tr, fr = reference_path.calculate_features(x.astype(np.float64), fs, settings)
+    path = sg.SpectrogramPath()
+    path.last_fs, path.last_settings = fs, settings
+    t, feat = path._calculate_features(x)
+    assert np.array_equal(t, tr) and feat.shape == fr.shape
+    assert np.max(np.abs(feat - fr)) <= 1e-4 / np.log(10) * 2      # log10 of a sum within 1e-4 relative
+
+
+def test_plot_extra_source_selection_and_combine():
+    a, fs = sweep(seed=3)
+    b, _ = sweep(seed=4)
+    path = sg.SpectrogramPath()
+    settings = dict(nperseg=512, fmin=0.0, fmax=100.0, log_scale=False, mode_proc="None", mode_raw="Both",
+                    draw_proc=False, draw_raw=True)
+    infos = [dict(signal_raw=a, signal_proc=None, fs=fs, item="s0"), dict(signal_raw=b, signal_proc=None, fs=fs, item="s1")]
+    cat = path.combine(infos, settings)
+    want, seg = stft_oracle.combine_sweeps([a, b], [fs, fs])
+    assert np.array_equal(cat, want)
+    assert [(s["start_time_combined"], s["end_time_combined"]) for s in path.segment_map] == seg
+    img = path.plot_extra(cat, None, fs, settings)
+    ref = reference_path.plot_spectrogram_compute(want.astype(np.float64), fs, settings)
+    assert path.spec_data_source is cat and np.array_equal(path.last_t, ref["last_t"])
+    assert_parity(path.last_Sxx, ref["last_Sxx"])
+    assert np.max(np.abs(img - ref["image"])) <= 1e-4

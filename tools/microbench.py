@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Device-resident timing of the STFT kernel over a grid of shapes (CUDA events,
+L2 defeated by working sets > 126 MB or an explicit flush).  Prints one JSON line
+per shape: samples/s, algorithmic GB/s, fraction of the measured HBM peak."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spectrogram_generator_b200 as sg  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def time_shape(batch, n, nperseg, hop, iters=10, window="hann", detrend="constant", dtype=torch.float32, flush=None):
+    plan = sg.triage(n, 1.0, window, nperseg, nperseg - hop, None, detrend, True, "density", "psd")
+    eng = sg.engine()
+    x = torch.randn((batch, n), device="cuda", dtype=dtype)
+    out = torch.empty((batch, plan.nframes, plan.nbins), device="cuda", dtype=torch.float32)
+    for _ in range(3):
+        eng.stft_psd(x, plan, out=out)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.stft_psd(x, plan, out=out)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.median(ts))
+    bytes_alg = x.element_size() * batch * n + 4 * batch * plan.nframes * plan.nbins
+    return dict(batch=batch, n=n, nperseg=nperseg, hop=hop, frames=plan.nframes, ms=round(ms, 4),
+                ms_min=round(min(ts), 4), gsamples_s=round(batch * n / ms / 1e6, 2),
+                gbs=round(bytes_alg / ms / 1e6, 1), frac=round(bytes_alg / ms / 1e6 / peak(), 4),
+                mb=round(bytes_alg / 1e6, 1))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--set", default="core")
+    args = ap.parse_args()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    shapes = []
+    if args.set in ("core", "all"):
+        shapes += [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 1024, 896),
+                   (1000, 40000, 1024, 512), (1000, 40000, 256, 64), (16, 5_760_000, 4096, 1024),
+                   (1, 172_800_000, 2048, 512), (1, 441_000, 1024, 256)]
+    if args.set in ("c5", "all"):
+        for nperseg in (256, 512, 1024, 2048, 4096, 8192, 16384):
+            for ov in (0.5, 0.75, 0.875):
+                shapes.append((1024, 100_000, nperseg, int(nperseg * (1 - ov))))
+    for s in shapes:
+        print(json.dumps(time_shape(*s, flush=flush)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
