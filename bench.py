@@ -63,22 +63,42 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max = index, False, [], set(), None
-
-    def run(self):
-        try:
+        self.h = None
+        try:                                     # NVML set-up happens before the timed region
             import pynvml
+            self.nv = pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            while not self.stop_flag:
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:      # pragma: no cover
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception as e:      # pragma: no cover
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.002)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max,
@@ -186,6 +206,7 @@ def run_gpu(args):
             dist.all_reduce(part)
         mean = part * (1.0 / total_sweeps)
     end.record()
+    sampler.sample()                 # all K steps are enqueued: this sample is taken under load
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -257,8 +278,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

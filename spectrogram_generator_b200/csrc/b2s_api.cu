@@ -59,7 +59,7 @@ int twiddles(int dev, int nperseg, const float2** out) {
     auto it = g_tw.find(key);
     if (it == g_tw.end()) {
         std::vector<float> host;
-        b2s::make_twiddles(nperseg, host);
+        b2s::make_tables(nperseg, host);
         float2* d = nullptr;
         cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
@@ -74,11 +74,11 @@ int twiddles(int dev, int nperseg, const float2** out) {
     return B2S_OK;
 }
 
-template <int LOG2N, typename Tin>
+template <int LOG2N, typename Tin, bool GENERAL>
 int launch_stft(const b2s::StftArgs& a, cudaStream_t stream) {
     using PL = b2s::Plan<LOG2N>;
     constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
-    auto kern = b2s::stft_psd_kernel<LOG2N, Tin, MINB>;
+    auto kern = b2s::stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>;
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
@@ -131,7 +131,10 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     }
     const int log2n = b2s::ilog2_exact(nperseg);
     int rc = B2S_ERR_UNSUPPORTED;
-#define B2S_RUN(L) rc = launch_stft<L, Tin>(a, (cudaStream_t)stream)
+    // the reference's call (linear power, every bin) takes the branch-free epilogue
+    const bool general = (out_mode != B2S_OUT_LINEAR) || kmin != 0 || kmax != nperseg / 2;
+#define B2S_RUN(L) \
+    rc = general ? launch_stft<L, Tin, true>(a, (cudaStream_t)stream) : launch_stft<L, Tin, false>(a, (cudaStream_t)stream)
     B2S_DISPATCH_LOG2N(log2n, B2S_RUN)
 #undef B2S_RUN
     return rc;

@@ -36,14 +36,27 @@ inline int ilog2_exact(int v) {
     return l;
 }
 
-// W_N^j = exp(-2 pi i j / N), j = 0..N-1, computed in double and rounded once.
-inline void make_twiddles(int N, std::vector<float>& out) {
-    out.resize(2 * (size_t)N);
-    for (int j = 0; j < N; ++j) {
-        const double a = 2.0 * M_PI * (double)j / (double)N;
-        out[2 * j] = (float)std::cos(a);
-        out[2 * j + 1] = (float)(-std::sin(a));
-    }
+// exp(-2 pi i num / den), computed in double and rounded once
+inline void put_w(std::vector<float>& out, size_t idx, long long num, long long den) {
+    const double a = 2.0 * M_PI * (double)(num % den) / (double)den;
+    out[2 * idx] = (float)std::cos(a);
+    out[2 * idx + 1] = (float)(-std::sin(a));
+}
+
+// The constant tables of Plan<LOG2N> (see b2s_kernels.cuh), as interleaved floats.
+template <int LOG2N>
+inline void make_tables_t(std::vector<float>& out) {
+    using PL = Plan<LOG2N>;
+    out.assign(2 * (size_t)PL::TABLE, 0.f);
+    if (PL::P >= 2)
+        for (int r = 1; r < 16; ++r)
+            for (int jm = 0; jm < 16; ++jm) put_w(out, PL::OFF_P1 + (r - 1) * 16 + jm, (long long)r * jm, 256);
+    if (PL::P == 3)
+        for (int r = 1; r < 16; ++r)
+            for (int jm = 0; jm < 256; ++jm) put_w(out, PL::OFF_P2 + (r - 1) * 256 + jm, (long long)r * jm, 4096);
+    for (int r = 1; r < PL::GF; ++r)
+        for (int k = 0; k < PL::NS; ++k) put_w(out, PL::OFF_FIN + (r - 1) * PL::NS + k, (long long)r * k, PL::M);
+    for (int k = 0; k <= PL::M; ++k) put_w(out, PL::OFF_POST + k, k, PL::N);
 }
 
 inline long long frames_available(long long n, int nperseg, int hop) {
@@ -135,4 +148,13 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
         default: break;                \
     }
 
+}  // namespace b2s
+
+namespace b2s {
+inline void make_tables(int nperseg, std::vector<float>& out) {
+    const int log2n = ilog2_exact(nperseg);
+#define B2S_TBL(L) make_tables_t<L>(out)
+    B2S_DISPATCH_LOG2N(log2n, B2S_TBL)
+#undef B2S_TBL
+}
 }  // namespace b2s

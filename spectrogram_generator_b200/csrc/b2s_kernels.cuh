@@ -36,7 +36,7 @@ struct StftParams {
     long long frame0;            // first (global) frame index of this launch
     long long out_batch_stride;  // elements between signals in `out`
     const float* window;         // [nperseg] fp32 window table, device
-    const float2* tw;            // [nperseg] W_N^j = (cos, -sin)(2 pi j / N), device
+    const float2* tw;            // [Plan::TABLE] twiddle tables (see Plan), device
     float* out;                  // [batch][nframes][kmax-kmin+1]
     int nframes;                 // frames per signal computed by this launch
     int chunk_frames;            // consecutive frames per work unit
@@ -63,6 +63,17 @@ struct Plan {
     static constexpr int BUF = M + (M >> 4) * 2;                 // padded complex slots
     static constexpr int RED = (G > 32) ? G / 32 : 1;            // mean partials per group
     static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * 2 * RED * sizeof(float);
+    // constant tables (complex entries, W = exp(-2 pi i ./.)), laid out so that
+    // consecutive lanes read consecutive entries:
+    //   P1  [15][16]    W_256^(r jm)           pass 1 (P >= 2)
+    //   P2  [15][256]   W_4096^(r jm)          pass 2 (P == 3)
+    //   FIN [GF-1][NS]  W_M^(r kappa)          final-stage butterflies
+    //   POST[M+1]       W_N^k                  real-FFT split
+    static constexpr int OFF_P1 = 0;
+    static constexpr int OFF_P2 = OFF_P1 + (P >= 2 ? 15 * 16 : 0);
+    static constexpr int OFF_FIN = OFF_P2 + (P == 3 ? 15 * 256 : 0);
+    static constexpr int OFF_POST = OFF_FIN + (GF - 1) * NS;
+    static constexpr int TABLE = OFF_POST + M + 1;
     static_assert(M >= 16, "nperseg >= 32");
     static_assert(GF == 1 || GF == 2 || GF == 4 || GF == 8, "plan");
 };
@@ -94,6 +105,8 @@ template <> struct Loader<double> {
 };
 
 // ---- epilogue helpers ---------------------------------------------------------
+// GENERAL = false: linear power, all bins (the reference's call) -- no per-bin branches.
+template <bool GENERAL>
 struct Epi {
     float* row;        // out + frame row (already offset by -kmin)
     float s_edge;      // scale            (DC / Nyquist)
@@ -101,8 +114,12 @@ struct Epi {
     float floor;
     int kmin, kmax, db;
     B2S_DEVICE void put(int k, float p) const {
-        if (db) p = 10.0f * log10f(fmaxf(p, floor));
-        if (k >= kmin && k <= kmax) row[k] = p;
+        if constexpr (GENERAL) {
+            if (db) p = 10.0f * log10f(fmaxf(p, floor));
+            if (k >= kmin && k <= kmax) row[k] = p;
+        } else {
+            row[k] = p;
+        }
     }
     // Z[k] = zk, Z[M-k] = zm, w = W_N^k : interior bins k and M-k
     B2S_DEVICE void pair(int k, int mk, float2 zk, float2 zm, float2 w) const {
@@ -151,7 +168,7 @@ B2S_DEVICE float group_mean(const float2 (&v)[16], unsigned gmask, int grp, int 
 }
 
 // ---- the kernel ------------------------------------------------------------------
-template <int LOG2N, typename Tin, int MINB>
+template <int LOG2N, typename Tin, int MINB, bool GENERAL>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const StftParams p) {
     using PL = Plan<LOG2N>;
     constexpr int M = PL::M, G = PL::G, NS = PL::NS, GF = PL::GF;
@@ -171,7 +188,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     for (int r = 0; r < 16; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(p.window) + (j + G * r));
 
     const int kout = p.kmax - p.kmin + 1;
-    Epi epi;
+    Epi<GENERAL> epi;
     epi.s_edge = p.scale;
     epi.s_int = 2.0f * p.scale;
     epi.floor = p.db_floor;
@@ -244,9 +261,9 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
                 const int jm = j & (Ns - 1);
 #pragma unroll
                 for (int r = 0; r < 16; ++r) v[r] = buf[phys(j + r * G)];
-                const int estep = 2 * jm * (M / (16 * Ns));      // table index step per r
+                const float2* const twp = p.tw + ((pass == 1) ? PL::OFF_P1 : PL::OFF_P2) + jm;
 #pragma unroll
-                for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(p.tw + r * estep));
+                for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], __ldg(twp + (r - 1) * Ns));
                 radix16(v);
                 group_sync<G>(gmask, grp);
                 const int base = (j - jm) * 16 + jm;
@@ -269,15 +286,15 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
                     }
 #pragma unroll
                     for (int r = 1; r < GF; ++r) {
-                        U[r] = cmul(U[r], __ldg(p.tw + 2 * r * kap));
-                        V[r] = cmul(V[r], __ldg(p.tw + 2 * r * kap2));
+                        U[r] = cmul(U[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * NS + kap));
+                        V[r] = cmul(V[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * NS + kap2));
                     }
                     SmallFft<GF>::run(U);
                     SmallFft<GF>::run(V);
 #pragma unroll
                     for (int a = 0; a < GF; ++a) {
                         const int k = kap + a * NS;
-                        epi.pair(k, M - k, U[a], V[GF - 1 - a], __ldg(p.tw + k));
+                        epi.pair(k, M - k, U[a], V[GF - 1 - a], __ldg(p.tw + PL::OFF_POST + k));
                     }
                 } else {
                     // kappa = 0 and kappa = NS/2 are their own mirrors
@@ -287,18 +304,18 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
                         V[r] = buf[phys(NS / 2 + r * NS)];
                     }
 #pragma unroll
-                    for (int r = 1; r < GF; ++r) V[r] = cmul(V[r], __ldg(p.tw + r * NS));
+                    for (int r = 1; r < GF; ++r) V[r] = cmul(V[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * NS + NS / 2));
                     SmallFft<GF>::run(U);
                     SmallFft<GF>::run(V);
                     epi.dc_nyq(M, U[0]);
 #pragma unroll
                     for (int a = 1; 2 * a < GF; ++a)
-                        epi.pair(a * NS, M - a * NS, U[a], U[GF - a], __ldg(p.tw + a * NS));
+                        epi.pair(a * NS, M - a * NS, U[a], U[GF - a], __ldg(p.tw + PL::OFF_POST + a * NS));
                     if constexpr (GF % 2 == 0) epi.self_mid(M / 2, U[GF / 2]);
 #pragma unroll
                     for (int a = 0; 2 * a < GF - 1; ++a) {
                         const int k = NS / 2 + a * NS;
-                        epi.pair(k, M - k, V[a], V[GF - 1 - a], __ldg(p.tw + k));
+                        epi.pair(k, M - k, V[a], V[GF - 1 - a], __ldg(p.tw + PL::OFF_POST + k));
                     }
                     if constexpr (GF % 2 == 1) epi.self_mid(NS / 2 + ((GF - 1) / 2) * NS, V[(GF - 1) / 2]);
                 }

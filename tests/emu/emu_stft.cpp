@@ -16,10 +16,14 @@ using namespace b2s;
 template <int LOG2N>
 static void run_one(const StftArgs& a, StftParams p, unsigned grid) {
     using PL = Plan<LOG2N>;
-    if (a.x_is_f64)
-        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1>(p); });
-    else
-        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1>(p); });
+    const bool general = a.out_mode != 0 || a.kmin != 0 || a.kmax != a.nperseg / 2;
+    if (a.x_is_f64) {
+        if (general) emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1, true>(p); });
+        else emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1, false>(p); });
+    } else {
+        if (general) emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1, true>(p); });
+        else emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1, false>(p); });
+    }
 }
 
 extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long long n, long long x_batch_stride,
@@ -38,7 +42,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
         p.n_units = p.units_per_signal * batch;
     }
     std::vector<float> tw;
-    make_twiddles(nperseg, tw);
+    make_tables(nperseg, tw);
     p.tw = reinterpret_cast<const float2*>(tw.data());
     if (p.n_units == 0) return 0;
 #define RUN(L) run_one<L>(a, p, (unsigned)grid)

@@ -32,11 +32,24 @@ def parity_report(S, So, floor=FLOOR):
                 finite=bool(np.isfinite(S).all()))
 
 
-def assert_parity(S, So, rel=REL_TOL, floor=FLOOR, abs_tol=ABS_TOL, db=DB_TOL, what=""):
+def assert_parity(S, So, rel=REL_TOL, floor=FLOOR, abs_tol=ABS_TOL, db=DB_TOL, what="", tail=0.0):
+    """The stated bar.  ``tail`` (default 0: every bin) is for multi-million-bin cases
+    only: the fraction of above-floor bins allowed between ``rel`` and ``2*rel`` -- the
+    worst of ~10^7 bins sitting 60 dB under a tone is a 5-sigma event of the fp32
+    rounding noise (DESIGN.md "fp32 floor"); nothing may exceed ``2*rel`` / ``2*db``."""
     r = parity_report(S, So, floor)
     assert r["finite"], f"{what}: non-finite values"
-    assert r["rel"] <= rel, f"{what}: rel err {r['rel']:.3e} > {rel} above the {floor:g}*max floor"
     assert r["abs"] <= abs_tol, f"{what}: abs err {r['abs']:.3e} * max > {abs_tol}"
+    if tail > 0.0:
+        S64, So64 = np.asarray(S, dtype=np.float64), np.asarray(So, dtype=np.float64)
+        big = So64 >= floor * So64.max()
+        relv = np.abs(S64[big] - So64[big]) / So64[big]
+        frac = float(np.mean(relv > rel))
+        r["tail_frac"] = frac
+        assert frac <= tail, f"{what}: {frac:.2e} of above-floor bins exceed rel {rel} (allowed {tail:.0e})"
+        assert r["rel"] <= 2 * rel and r["db"] <= 2 * db, f"{what}: worst bin rel {r['rel']:.3e} / {r['db']:.2e} dB"
+        return r
+    assert r["rel"] <= rel, f"{what}: rel err {r['rel']:.3e} > {rel} above the {floor:g}*max floor"
     assert r["db"] <= db, f"{what}: dB err {r['db']:.3e} > {db}"
     return r
 

@@ -57,6 +57,12 @@ def main():
         shapes += [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 1024, 896),
                    (1000, 40000, 1024, 512), (1000, 40000, 256, 64), (16, 5_760_000, 4096, 1024),
                    (1, 172_800_000, 2048, 512), (1, 441_000, 1024, 256)]
+    if args.set == "c2":
+        shapes += [(1000, 40000, 512, 128)]
+    if args.set == "c4":
+        shapes += [(16, 5_760_000, 4096, 1024)]
+    if args.set == "n1024":
+        shapes += [(1000, 40000, 1024, 256)]
     if args.set in ("c5", "all"):
         for nperseg in (256, 512, 1024, 2048, 4096, 8192, 16384):
             for ov in (0.5, 0.75, 0.875):
