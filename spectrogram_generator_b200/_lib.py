@@ -49,7 +49,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise B2SError("nvcc not found: cannot build libb200stft.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB_PATH]
+    extra = ["-DB2S_EXPERIMENTS"] if os.environ.get("B2S_EXPERIMENTS") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise B2SError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -3,6 +3,7 @@
 // per-(device, nperseg) twiddle tables.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -10,7 +11,7 @@
 #include <vector>
 
 #include "../../include/b2s.h"
-#include "b2s_host.hpp"
+#include "b2s_dispatch.hpp"
 
 namespace {
 
@@ -74,46 +75,95 @@ int twiddles(int dev, int nperseg, const float2** out) {
     return B2S_OK;
 }
 
-template <int LOG2N, typename Tin, bool GENERAL>
-int launch_stft(const b2s::StftArgs& a, cudaStream_t stream) {
-    using PL = b2s::Plan<LOG2N>;
-    constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
-    auto kern = b2s::stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>;
+struct KernelState {
+    int occ = 0;
+    int dev = -1;
+};
+std::map<const void*, KernelState> g_kern;     // guarded by g_mu
+
+// One launch of an STFT kernel (either family): persistent grid sized from the
+// occupancy, work units sized from the grid (b2s::plan_stft).
+int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream) {
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-
-    static thread_local int configured_dev = -1;   // per instantiation
-    static thread_local int occ = 0;
-    if (configured_dev != dev) {
-        if ((int)PL::SMEM > di.smem_optin)
-            return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this nperseg");
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PL::SMEM);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PL::NT, PL::SMEM);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-        if (occ < 1) occ = 1;
-        configured_dev = dev;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        KernelState& ks = g_kern[kern];
+        if (ks.dev != dev) {
+            if ((int)smem > di.smem_optin)
+                return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this nperseg");
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, nt, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            if (ks.occ < 1) ks.occ = 1;
+            ks.dev = dev;
+        }
+        occ = ks.occ;
     }
     const long long resident_ctas = (long long)di.sm_count * occ;
-
     b2s::StftParams p{};
     std::string err;
-    rc = b2s::plan_stft(a, PL::FPC, resident_ctas * PL::FPC, p, err);
+    rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
     rc = twiddles(dev, a.nperseg, &p.tw);
     if (rc != B2S_OK) return rc;
-
-    // persistent grid: a whole number of waves, never more CTAs than work
-    long long need = (p.n_units + PL::FPC - 1) / PL::FPC;
-    long long grid = (need < resident_ctas) ? need : resident_ctas;
-    kern<<<(unsigned)grid, PL::NT, PL::SMEM, stream>>>(p);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "stft_psd_kernel launch");
+    // persistent grid: never more CTAs than work
+    const long long need = (p.n_units + fpc - 1) / fpc;
+    const long long grid = (need < resident_ctas) ? need : resident_ctas;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)nt), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stft kernel launch");
     return B2S_OK;
 }
+
+struct CudaLauncher {
+    cudaStream_t stream;
+    template <int LOG2N, typename Tin, int SHIFT, bool GENERAL>
+    int warp(const b2s::StftArgs& a) {
+        using WP = b2s::WarpPlan<LOG2N>;
+#ifdef B2S_EXPERIMENTS
+        // A/B variants for tuning runs (tools/microbench.py --variant): selected by B2S_VARIANT
+        if constexpr ((LOG2N == 9 || LOG2N == 10) && SHIFT == 4 && !GENERAL && sizeof(Tin) == 4) {
+            const char* v = getenv("B2S_VARIANT");
+            const int vi = v ? atoi(v) : 0;
+            if (vi == 1) {
+                using W2 = b2s::WarpPlan<LOG2N, 128>;
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 3, true>,
+                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
+            }
+            if (vi == 2) {
+                using W2 = b2s::WarpPlan<LOG2N, 256>;
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 256, 1, true>,
+                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
+            }
+            if (vi == 3) {
+                using W2 = b2s::WarpPlan<LOG2N, 128>;
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 4, false>,
+                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
+            }
+            if (vi == 4) {
+                using W2 = b2s::WarpPlan<LOG2N, 128>;
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 2, true>,
+                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
+            }
+        }
+#endif
+        return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>, WP::NT, WP::SMEM,
+                          WP::FPC, a, stream);
+    }
+    template <int LOG2N, typename Tin, bool GENERAL>
+    int cta(const b2s::StftArgs& a) {
+        using PL = b2s::Plan<LOG2N>;
+        constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
+        return launch_any((const void*)b2s::stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>, PL::NT, PL::SMEM, PL::FPC,
+                          a, stream);
+    }
+};
 
 template <typename Tin>
 int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
@@ -129,15 +179,8 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
         int rc = b2s::plan_stft(a, 1, 1, p, err);
         if (rc < 0) return fail(rc, err);
     }
-    const int log2n = b2s::ilog2_exact(nperseg);
-    int rc = B2S_ERR_UNSUPPORTED;
-    // the reference's call (linear power, every bin) takes the branch-free epilogue
-    const bool general = (out_mode != B2S_OUT_LINEAR) || kmin != 0 || kmax != nperseg / 2;
-#define B2S_RUN(L) \
-    rc = general ? launch_stft<L, Tin, true>(a, (cudaStream_t)stream) : launch_stft<L, Tin, false>(a, (cudaStream_t)stream)
-    B2S_DISPATCH_LOG2N(log2n, B2S_RUN)
-#undef B2S_RUN
-    return rc;
+    CudaLauncher L{(cudaStream_t)stream};
+    return b2s::dispatch_stft(a, L);
 }
 
 }  // namespace

@@ -1,0 +1,73 @@
+// Kernel selection shared by the CUDA library and the emulator harness.
+//
+//   nperseg <= 1024 : stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>
+//       SHIFT = hop*16/nperseg in {2,4,8,14} (float samples, 2-element aligned frames,
+//       nperseg >= 256) selects the sliding-register-window variant, 0 otherwise;
+//   nperseg >= 2048 : stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>  (multi-warp groups).
+//
+// A Launcher provides
+//   template <int LOG2N, typename Tin, int SHIFT, bool GENERAL> int warp(const StftArgs&);
+//   template <int LOG2N, typename Tin, bool GENERAL>            int cta(const StftArgs&);
+#pragma once
+
+#include "b2s_host.hpp"
+#include "b2s_warp_kernel.cuh"
+
+namespace b2s {
+
+inline bool frames_vec_aligned(const StftArgs& a) {
+    const size_t esz = a.x_is_f64 ? 8 : 4;
+    const bool base_ok = (reinterpret_cast<uintptr_t>(a.x) % (2 * esz)) == 0;
+    return base_ok && (a.hop % 2 == 0) && (a.x_batch_stride % 2 == 0 || a.batch <= 1);
+}
+
+inline int sliding_shift(const StftArgs& a, int log2n) {
+    if (a.x_is_f64 || log2n < 8 || log2n > 10 || !frames_vec_aligned(a)) return 0;
+    const long long n16 = a.nperseg / 16;
+    if (a.hop % n16) return 0;
+    const long long s = a.hop / n16;
+    return (s == 2 || s == 4 || s == 8 || s == 14) ? (int)s : 0;
+}
+
+template <int LOG2N, typename Tin, bool GENERAL, class Launcher>
+int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
+    if constexpr (LOG2N >= 8 && sizeof(Tin) == 4) {
+        switch (shift) {
+            case 2: return L.template warp<LOG2N, Tin, 2, GENERAL>(a);
+            case 4: return L.template warp<LOG2N, Tin, 4, GENERAL>(a);
+            case 8: return L.template warp<LOG2N, Tin, 8, GENERAL>(a);
+            case 14: return L.template warp<LOG2N, Tin, 14, GENERAL>(a);
+            default: break;
+        }
+    }
+    return L.template warp<LOG2N, Tin, 0, GENERAL>(a);
+}
+
+template <typename Tin, bool GENERAL, class Launcher>
+int dispatch_tg(const StftArgs& a, Launcher& L) {
+    const int log2n = ilog2_exact(a.nperseg);
+    const int shift = sliding_shift(a, log2n);
+    switch (log2n) {
+        case 5: return dispatch_warp_shift<5, Tin, GENERAL>(a, L, shift);
+        case 6: return dispatch_warp_shift<6, Tin, GENERAL>(a, L, shift);
+        case 7: return dispatch_warp_shift<7, Tin, GENERAL>(a, L, shift);
+        case 8: return dispatch_warp_shift<8, Tin, GENERAL>(a, L, shift);
+        case 9: return dispatch_warp_shift<9, Tin, GENERAL>(a, L, shift);
+        case 10: return dispatch_warp_shift<10, Tin, GENERAL>(a, L, shift);
+        case 11: return L.template cta<11, Tin, GENERAL>(a);
+        case 12: return L.template cta<12, Tin, GENERAL>(a);
+        case 13: return L.template cta<13, Tin, GENERAL>(a);
+        case 14: return L.template cta<14, Tin, GENERAL>(a);
+        default: return B2S_ERR_UNSUPPORTED;
+    }
+}
+
+template <class Launcher>
+int dispatch_stft(const StftArgs& a, Launcher& L) {
+    // the reference's call (linear power, every bin) takes the branch-free epilogue
+    const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
+    if (a.x_is_f64) return general ? dispatch_tg<double, true>(a, L) : dispatch_tg<double, false>(a, L);
+    return general ? dispatch_tg<float, true>(a, L) : dispatch_tg<float, false>(a, L);
+}
+
+}  // namespace b2s

@@ -18,12 +18,14 @@
 #define B2S_GLOBAL inline
 #define B2S_LAUNCH_BOUNDS(a, b)
 #define B2S_DYN_SMEM(name) unsigned char* const name = emu::dyn_smem()
+#define B2S_DYN_SMEM_F2(name) float2* const name = reinterpret_cast<float2*>(emu::dyn_smem())
 #else
 #define B2S_HD __host__ __device__ __forceinline__
 #define B2S_DEVICE __device__ __forceinline__
 #define B2S_GLOBAL __global__
 #define B2S_LAUNCH_BOUNDS(a, b) __launch_bounds__(a, b)
 #define B2S_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define B2S_DYN_SMEM_F2(name) extern __shared__ __align__(16) float2 name[]
 // named barrier over `n` threads (n a multiple of 32), id 1..15
 __device__ __forceinline__ void b2s_bar_sync(int id, int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");

@@ -113,12 +113,13 @@ struct Epi {
     float s_int;       // 2*scale          (interior bins)
     float floor;
     int kmin, kmax, db;
+    bool act = true;   // false: the group is past its last frame (warp kernel), stores are predicated off
     B2S_DEVICE void put(int k, float p) const {
         if constexpr (GENERAL) {
             if (db) p = 10.0f * log10f(fmaxf(p, floor));
-            if (k >= kmin && k <= kmax) row[k] = p;
+            if (act && k >= kmin && k <= kmax) row[k] = p;
         } else {
-            row[k] = p;
+            if (act) row[k] = p;
         }
     }
     // Z[k] = zk, Z[M-k] = zm, w = W_N^k : interior bins k and M-k

@@ -262,6 +262,89 @@ def _to_host(d: torch.Tensor, dtype) -> np.ndarray:
     return a if a.dtype == dtype else a.astype(dtype)
 
 
+_PIPE_CHUNK_BYTES = 32 << 20       # output bytes per pipeline stage
+
+
+class _Streams:
+    """Copy-in / copy-out side streams per device, created on first use."""
+    _by_dev = {}
+
+    @classmethod
+    def get(cls, dev: torch.device):
+        s = cls._by_dev.get(dev.index)
+        if s is None:
+            with torch.cuda.device(dev):
+                s = (torch.cuda.Stream(), torch.cuda.Stream())
+            cls._by_dev[dev.index] = s
+        return s
+
+
+def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=True, want_sum=False,
+                   kmin=0, kmax=None, out_mode=0, db_floor=0.0):
+    """Host arrays in, host arrays out: H2D copy, kernels and D2H copy of successive
+    chunks overlap on three streams (PCIe is full duplex), so the end-to-end time tends
+    to max(H2D, D2H) instead of their sum.  Chunks are runs of sweeps for batches and
+    frame ranges (with their nperseg-hop halo of samples) for a single long recording.
+    Returns (S_host [B, F, Kout] or None, sum_dev [F, Kout] or None)."""
+    eng = engine()
+    B, n = x2d.shape
+    kmax = plan.nbins - 1 if kmax is None else kmax
+    kout = kmax - kmin + 1
+    F = plan.nframes
+    if not x2d.flags.c_contiguous:
+        x2d = np.ascontiguousarray(x2d)
+    h_in = _as_host_tensor(x2d)
+    pinned = h_in.is_pinned()
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream()
+        s_in, s_out = _Streams.get(dev)
+        x_d = torch.empty((B, n), dtype=h_in.dtype, device=dev)
+        S_d = torch.empty((B, F, kout), dtype=torch.float32, device=dev)
+        h_out = torch.empty((B, F, kout), dtype=torch.float32, pin_memory=True) if per_sweep else None
+        row_bytes = F * kout * 4
+        # work items: (b0, b1, f0, f1)
+        items = []
+        if B * row_bytes <= _PIPE_CHUNK_BYTES or not per_sweep:
+            items.append((0, B, 0, F))
+        elif B >= 4:
+            step = max(1, _PIPE_CHUNK_BYTES // row_bytes)
+            items = [(b, min(B, b + step), 0, F) for b in range(0, B, step)]
+        else:
+            fstep = max(1, _PIPE_CHUNK_BYTES // (kout * 4))
+            items = [(b, b + 1, f, min(F, f + fstep)) for b in range(B) for f in range(0, F, fstep)]
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        for (b0, b1, f0, f1) in items:
+            lo, hi = (0, n) if (f0 == 0 and f1 == F) else (f0 * plan.hop, (f1 - 1) * plan.hop + plan.nperseg)
+            with torch.cuda.stream(s_in):
+                x_d[b0:b1, lo:hi].copy_(h_in[b0:b1, lo:hi], non_blocking=pinned)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            cur.wait_event(ev_in)
+            if f0 == 0 and f1 == F:
+                eng.stft_psd(x_d[b0:b1], plan, out=S_d[b0:b1], kmin=kmin, kmax=kmax, out_mode=out_mode,
+                             db_floor=db_floor)
+            else:
+                eng.stft_psd(x_d[b0:b1], plan, out=S_d[b0:b1, f0:f1], kmin=kmin, kmax=kmax,
+                             out_mode=out_mode, db_floor=db_floor, frame0=f0, nframes=f1 - f0)
+            if per_sweep:
+                ev_k = torch.cuda.Event()
+                ev_k.record(cur)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_k)
+                    h_out[b0:b1, f0:f1].copy_(S_d[b0:b1, f0:f1], non_blocking=True)
+        total = eng.batch_sum(S_d, 1.0) if want_sum else None
+        if per_sweep:
+            s_out.synchronize()
+        cur.synchronize()             # x_d / S_d were used on side streams: keep them alive until here
+    S = None
+    if per_sweep:
+        S = h_out.numpy()
+        if S.dtype != out_dtype:
+            S = S.astype(out_dtype)
+    return S, total
+
+
 # --------------------------------------------------------------------------
 # public API
 # --------------------------------------------------------------------------
@@ -290,10 +373,8 @@ def spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=None, n
     if B == 0 or plan.nframes == 0:
         S = np.empty(lead + (plan.nframes, plan.nbins), dtype=out_dtype)
     else:
-        xd = _to_device(x.reshape(B, plan.n), dev)
-        with torch.cuda.device(dev):
-            Sd = eng.stft_psd(xd, plan)
-            S = _to_host(Sd, out_dtype).reshape(lead + (plan.nframes, plan.nbins))
+        S, _ = _host_pipeline(x.reshape(B, plan.n), plan, dev, out_dtype)
+        S = S.reshape(lead + (plan.nframes, plan.nbins))
     # SciPy rolls the frequency axis back to where the data axis was and leaves
     # the segment-time axis last (:2334-2341); for axis=-1 that is the
     # [..., bin, frame] transposed view of the [..., frame, bin] buffer.
@@ -331,13 +412,11 @@ def mean_spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=No
     eng = engine()
     eng.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    S, total = _host_pipeline(x, plan, dev, out_dtype, per_sweep=return_per_sweep, want_sum=True)
     with torch.cuda.device(dev):
-        xd = _to_device(x, dev)
-        Sd = eng.stft_psd(xd, plan)
-        Md = eng.batch_sum(Sd, 1.0 / x.shape[0])
-        mean = np.moveaxis(_to_host(Md, out_dtype), -1, -2)
-        if return_per_sweep:
-            return f, t, mean, np.moveaxis(_to_host(Sd, out_dtype), -1, -2)
+        mean = np.moveaxis(_to_host(total * (1.0 / x.shape[0]), out_dtype), -1, -2)
+    if return_per_sweep:
+        return f, t, mean, np.moveaxis(S, -1, -2)
     return f, t, mean
 
 

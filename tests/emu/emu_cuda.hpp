@@ -101,5 +101,21 @@ inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src_lane) { return emu::shfl_idx(mask, v, src_lane); }
 
+inline int __any_sync(unsigned mask, int pred) {
+    const unsigned base = threadIdx.x & ~31u;
+    const int mine = pred ? 1 : 0;
+    std::memcpy(emu::g_cta->slots[threadIdx.x].data(), &mine, sizeof(int));
+    emu::warp_sync(mask);
+    int any = 0;
+    for (unsigned l = 0; l < 32; ++l) {
+        if (!((mask >> l) & 1u)) continue;
+        int v;
+        std::memcpy(&v, emu::g_cta->slots[base + l].data(), sizeof(int));
+        any |= v;
+    }
+    emu::warp_sync(mask);
+    return any;
+}
+
 template <typename T>
 inline T __ldg(const T* p) { return *p; }

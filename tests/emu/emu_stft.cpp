@@ -9,46 +9,49 @@ dim3_ blockDim;
 dim3_ gridDim;
 namespace emu { Cta* g_cta = nullptr; }
 
-#include "b2s_host.hpp"
+#include "b2s_dispatch.hpp"
 
 using namespace b2s;
 
-template <int LOG2N>
-static void run_one(const StftArgs& a, StftParams p, unsigned grid) {
-    using PL = Plan<LOG2N>;
-    const bool general = a.out_mode != 0 || a.kmin != 0 || a.kmax != a.nperseg / 2;
-    if (a.x_is_f64) {
-        if (general) emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1, true>(p); });
-        else emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, double, 1, false>(p); });
-    } else {
-        if (general) emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1, true>(p); });
-        else emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, float, 1, false>(p); });
+struct EmuLauncher {
+    StftParams p;
+    unsigned grid;
+    template <int LOG2N, typename Tin, int SHIFT, bool GENERAL>
+    int warp(const StftArgs&) {
+        using WP = WarpPlan<LOG2N>;
+        emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>(p); });
+        return 0;
     }
-}
+    template <int LOG2N, typename Tin, bool GENERAL>
+    int cta(const StftArgs&) {
+        using PL = Plan<LOG2N>;
+        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, Tin, 1, GENERAL>(p); });
+        return 0;
+    }
+};
 
+// force_shift: -1 = the library's own choice, 0 = disable the sliding variant
 extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long long n, long long x_batch_stride,
                             int nperseg, int hop, const float* window, int detrend, double scale, int out_mode,
                             float db_floor, int kmin, int kmax, long long frame0, long long nframes, float* out,
                             long long out_batch_stride, int grid, int force_chunk) {
     StftArgs a{x, x_is_f64, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
                db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride};
-    StftParams p{};
+    EmuLauncher L;
+    L.grid = (unsigned)grid;
     std::string err;
-    const int log2n = plan_stft(a, 1, (long long)grid * 4, p, err);
+    const int log2n = plan_stft(a, 1, (long long)grid * 4, L.p, err);
     if (log2n < 0) return log2n;
     if (force_chunk > 0) {
-        p.chunk_frames = force_chunk;
-        p.units_per_signal = (nframes + force_chunk - 1) / force_chunk;
-        p.n_units = p.units_per_signal * batch;
+        L.p.chunk_frames = force_chunk;
+        L.p.units_per_signal = (nframes + force_chunk - 1) / force_chunk;
+        L.p.n_units = L.p.units_per_signal * batch;
     }
     std::vector<float> tw;
     make_tables(nperseg, tw);
-    p.tw = reinterpret_cast<const float2*>(tw.data());
-    if (p.n_units == 0) return 0;
-#define RUN(L) run_one<L>(a, p, (unsigned)grid)
-    B2S_DISPATCH_LOG2N(log2n, RUN)
-#undef RUN
-    return 0;
+    L.p.tw = reinterpret_cast<const float2*>(tw.data());
+    if (L.p.n_units == 0) return 0;
+    return dispatch_stft(a, L);
 }
 
 extern "C" int emu_batch_sum(const float* in, long long in_stride, int batch, int rows_per_slab, long long elems,
