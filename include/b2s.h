@@ -45,10 +45,10 @@ extern "C" {
 int b2s_version(void);
 const char* b2s_last_error(void);
 
-/* 1 if `nperseg` runs on the fused radix-16 Stockham kernel (powers of two in
- * [32, 16384]), 2 if it runs on the direct-DFT kernel (any other 2..8192:
- * the GUI spin box allows any integer 32..8192, GUI.py:87-89, and SciPy clamps
- * nperseg to len(x), _spectral_py.py:2443-2447), 0 if unsupported. */
+/* 1 if `nperseg` runs on the fused radix-16 Stockham kernels (powers of two in
+ * [32, 16384]), 2 if it runs on the direct-DFT kernel (every other length in
+ * 1..16384: the GUI spin box allows any integer 32..8192, GUI.py:87-89, and SciPy
+ * clamps nperseg to len(x), _spectral_py.py:2443-2447), 0 if unsupported. */
 int b2s_nperseg_support(int nperseg);
 
 /* Frames SciPy produces for a signal of n samples: (n - nperseg)//hop + 1
@@ -97,6 +97,23 @@ int b2s_stft_psd_f64(const double* x, long long batch, long long n, long long x_
                      float* out, long long out_batch_stride, void* stream);
 
 /*
+ * Fused band-power feature (PlotEngine._calculate_features, PlotEngine.py:229-239):
+ * the same spectrogram, but instead of storing [frame][bin] the bins kmin..kmax of
+ * every frame are summed in the epilogue -- out is [batch][nframes] fp32 (signal b at
+ * out + b*out_batch_stride).  The HMM path needs only these F numbers, so the
+ * 4*F*K bytes of spectrogram output are never written.  log10 and the first
+ * difference (PlotEngine.py:240-242) stay on the host (F values).
+ */
+int b2s_stft_band_power_f32(const float* x, long long batch, long long n, long long x_batch_stride,
+                            int nperseg, int hop, const float* window, int detrend, double scale,
+                            int kmin, int kmax, long long frame0, long long nframes,
+                            float* out, long long out_batch_stride, void* stream);
+int b2s_stft_band_power_f64(const double* x, long long batch, long long n, long long x_batch_stride,
+                            int nperseg, int hop, const float* window, int detrend, double scale,
+                            int kmin, int kmax, long long frame0, long long nframes,
+                            float* out, long long out_batch_stride, void* stream);
+
+/*
  * Cross-sweep sum / mean (BASELINE config 2; the reference has no code for it,
  * SURVEY.md 8 a-15): out[e] = post_scale * sum_b in[b*in_batch_stride + e],
  * summed in a fixed order (deterministic).  `scratch` must hold
@@ -105,6 +122,15 @@ int b2s_stft_psd_f64(const double* x, long long batch, long long n, long long x_
 long long b2s_batch_sum_scratch_elems(long long batch, long long elems);
 int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long long in_batch_stride,
                       float* out, float* scratch, float post_scale, void* stream);
+
+/*
+ * Display scaling of a (cropped) spectrogram on the device -- PlotEngine._plot_spectrogram,
+ * PlotEngine.py:126-131: out = clip(S/(base+1e-20), 0, 1) with base = max(S) (or global_max
+ * when > 0); with log_scale, 10*log10(out+1e-12) min-max normalised to [0,1] (zeros when the
+ * dB range is <= 1e-6).  `scratch` holds 2 unsigned ints (device).  S and out: `elems` floats.
+ */
+int b2s_display_scale_f32(const float* s, long long elems, int log_scale, float global_max, float* out,
+                          unsigned int* scratch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,9 @@ _lib = None
 _STFT_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_p, c_int, c_double,
               c_int, c_float, c_int, c_int, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p]
 
+_BAND_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_p, c_int, c_double,
+              c_int, c_int, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p]
+
 # name -> (restype, argtypes); must list every symbol include/b2s.h declares
 SIGNATURES = {
     "b2s_version": (c_int, []),
@@ -72,9 +75,12 @@ SIGNATURES = {
     "b2s_frame_count": (c_longlong, [c_longlong, c_int, c_int]),
     "b2s_stft_psd_f32": (c_int, _STFT_ARGS),
     "b2s_stft_psd_f64": (c_int, _STFT_ARGS),
+    "b2s_stft_band_power_f32": (c_int, _BAND_ARGS),
+    "b2s_stft_band_power_f64": (c_int, _BAND_ARGS),
     "b2s_batch_sum_scratch_elems": (c_longlong, [c_longlong, c_longlong]),
     "b2s_batch_sum_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p,
                                   c_float, c_void_p]),
+    "b2s_display_scale_f32": (c_int, [c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -33,7 +33,7 @@ struct DeviceInfo {
 
 std::mutex g_mu;
 std::map<int, DeviceInfo> g_dev;
-std::map<std::pair<int, int>, float2*> g_tw;     // (device, nperseg) -> W_N table
+std::map<std::pair<int, int>, float2*> g_tw;     // (device, +-nperseg) -> tables (negative: direct-DFT table)
 
 int device_info(DeviceInfo& out, int& dev) {
     cudaError_t e = cudaGetDevice(&dev);
@@ -54,13 +54,14 @@ int device_info(DeviceInfo& out, int& dev) {
 
 // Twiddle table for nperseg on the current device; built on the host in double,
 // uploaded once (synchronously, first use only) and cached for the process.
-int twiddles(int dev, int nperseg, const float2** out) {
+int twiddles(int dev, int nperseg, bool dft, const float2** out) {
     std::lock_guard<std::mutex> g(g_mu);
-    auto key = std::make_pair(dev, nperseg);
+    auto key = std::make_pair(dev, dft ? -nperseg : nperseg);
     auto it = g_tw.find(key);
     if (it == g_tw.end()) {
         std::vector<float> host;
-        b2s::make_tables(nperseg, host);
+        if (dft) b2s::make_dft_table(nperseg, host);
+        else b2s::make_tables(nperseg, host);
         float2* d = nullptr;
         cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(twiddles)");
@@ -110,7 +111,7 @@ int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftAr
     rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
-    rc = twiddles(dev, a.nperseg, &p.tw);
+    rc = twiddles(dev, a.nperseg, false, &p.tw);
     if (rc != B2S_OK) return rc;
     // persistent grid: never more CTAs than work
     const long long need = (p.n_units + fpc - 1) / fpc;
@@ -121,9 +122,42 @@ int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftAr
     return B2S_OK;
 }
 
+// direct-DFT family: one CTA per frame, grid-stride
+template <typename Tin>
+int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const void* kern = (const void*)b2s::dft_psd_kernel<Tin>;
+    const size_t smem = b2s::dft_smem_bytes(a.nperseg);
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        KernelState& ks = g_kern[kern];
+        if (ks.dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            ks.dev = dev;
+            ks.occ = 1;
+        }
+    }
+    if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: nperseg too large for the direct-DFT kernel");
+    b2s::DftParams p{};
+    b2s::fill_dft_params(a, p);
+    if (p.total_frames == 0) return B2S_OK;
+    rc = twiddles(dev, a.nperseg, true, &p.tw);
+    if (rc != B2S_OK) return rc;
+    const long long cap = (long long)di.sm_count * 8;
+    const long long grid = p.total_frames < cap ? p.total_frames : cap;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(b2s::kDftThreads), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "dft kernel launch");
+    return B2S_OK;
+}
+
 struct CudaLauncher {
     cudaStream_t stream;
-    template <int LOG2N, typename Tin, int SHIFT, bool GENERAL>
+    template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const b2s::StftArgs& a) {
         using WP = b2s::WarpPlan<LOG2N>;
 #ifdef B2S_EXPERIMENTS
@@ -133,34 +167,34 @@ struct CudaLauncher {
             const int vi = v ? atoi(v) : 0;
             if (vi == 1) {
                 using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 3, true>,
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 3, true>,
                                   W2::NT, W2::SMEM, W2::FPC, a, stream);
             }
             if (vi == 2) {
                 using W2 = b2s::WarpPlan<LOG2N, 256>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 256, 1, true>,
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 256, 1, true>,
                                   W2::NT, W2::SMEM, W2::FPC, a, stream);
             }
             if (vi == 3) {
                 using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 4, false>,
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 4, false>,
                                   W2::NT, W2::SMEM, W2::FPC, a, stream);
             }
             if (vi == 4) {
                 using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL, 128, 2, true>,
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 2, true>,
                                   W2::NT, W2::SMEM, W2::FPC, a, stream);
             }
         }
 #endif
-        return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>, WP::NT, WP::SMEM,
+        return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>, WP::NT, WP::SMEM,
                           WP::FPC, a, stream);
     }
-    template <int LOG2N, typename Tin, bool GENERAL>
+    template <int LOG2N, typename Tin, int MODE>
     int cta(const b2s::StftArgs& a) {
         using PL = b2s::Plan<LOG2N>;
         constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
-        return launch_any((const void*)b2s::stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>, PL::NT, PL::SMEM, PL::FPC,
+        return launch_any((const void*)b2s::stft_psd_kernel<LOG2N, Tin, MINB, MODE>, PL::NT, PL::SMEM, PL::FPC,
                           a, stream);
     }
 };
@@ -169,16 +203,16 @@ template <typename Tin>
 int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
                const float* window, int detrend, double scale, int out_mode, float db_floor, int kmin,
                int kmax, long long frame0, long long nframes, float* out, long long out_batch_stride,
-               void* stream) {
+               void* stream, int band_mode = 0) {
     b2s::StftArgs a{x, (int)(sizeof(Tin) == 8), batch, n, x_batch_stride, nperseg, hop, window, detrend,
-                    scale, out_mode, db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride};
+                    scale, out_mode, db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, band_mode};
     // validate before touching the device so bad arguments are reported as such
     {
-        b2s::StftParams p{};
         std::string err;
-        int rc = b2s::plan_stft(a, 1, 1, p, err);
+        int rc = b2s::validate_args(a, err);
         if (rc < 0) return fail(rc, err);
     }
+    if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
     CudaLauncher L{(cudaStream_t)stream};
     return b2s::dispatch_stft(a, L);
 }
@@ -191,11 +225,7 @@ int b2s_version(void) { return B2S_ABI_VERSION; }
 
 const char* b2s_last_error(void) { return g_err.c_str(); }
 
-int b2s_nperseg_support(int nperseg) {
-    const int l = b2s::ilog2_exact(nperseg);
-    if (l >= 5 && l <= 14) return 1;
-    return 0;
-}
+int b2s_nperseg_support(int nperseg) { return b2s::nperseg_support(nperseg); }
 
 long long b2s_frame_count(long long n, int nperseg, int hop) {
     if (nperseg < 1 || hop < 1) return 0;
@@ -216,6 +246,22 @@ int b2s_stft_psd_f64(const double* x, long long batch, long long n, long long x_
                      long long out_batch_stride, void* stream) {
     return stft_entry<double>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
                               db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, stream);
+}
+
+int b2s_stft_band_power_f32(const float* x, long long batch, long long n, long long x_batch_stride, int nperseg,
+                            int hop, const float* window, int detrend, double scale, int kmin, int kmax,
+                            long long frame0, long long nframes, float* out, long long out_batch_stride,
+                            void* stream) {
+    return stft_entry<float>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR,
+                             0.f, kmin, kmax, frame0, nframes, out, out_batch_stride, stream, 1);
+}
+
+int b2s_stft_band_power_f64(const double* x, long long batch, long long n, long long x_batch_stride, int nperseg,
+                            int hop, const float* window, int detrend, double scale, int kmin, int kmax,
+                            long long frame0, long long nframes, float* out, long long out_batch_stride,
+                            void* stream) {
+    return stft_entry<double>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR,
+                              0.f, kmin, kmax, frame0, nframes, out, out_batch_stride, stream, 1);
 }
 
 static const int kSumSlabRows = 64;
@@ -246,6 +292,26 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
+    return B2S_OK;
+}
+
+
+int b2s_display_scale_f32(const float* s, long long elems, int log_scale, float global_max, float* out,
+                          unsigned int* scratch, void* stream) {
+    if (!s || !out || !scratch || elems < 1) return fail(B2S_ERR_BAD_ARG, "b2s_display_scale_f32: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const int block = 256;
+    long long want = (elems + block - 1) / block;
+    const unsigned grid = (unsigned)(want < (long long)di.sm_count * 8 ? want : (long long)di.sm_count * 8);
+    b2s::minmax_init_kernel<<<1, 1, 0, st>>>(scratch);
+    b2s::minmax_kernel<<<grid, block, 0, st>>>(s, elems, scratch);
+    b2s::display_scale_kernel<<<grid, block, 0, st>>>(s, elems, scratch, log_scale ? 1 : 0, global_max, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "display_scale kernels");
     return B2S_OK;
 }
 

@@ -1,13 +1,13 @@
 // Kernel selection shared by the CUDA library and the emulator harness.
 //
-//   nperseg <= 1024 : stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>
+//   nperseg <= 1024 : stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>
 //       SHIFT = hop*16/nperseg in {2,4,8,14} (float samples, 2-element aligned frames,
 //       nperseg >= 256) selects the sliding-register-window variant, 0 otherwise;
-//   nperseg >= 2048 : stft_psd_kernel<LOG2N, Tin, MINB, GENERAL>  (multi-warp groups).
+//   nperseg >= 2048 : stft_psd_kernel<LOG2N, Tin, MINB, MODE>  (multi-warp groups).
 //
 // A Launcher provides
-//   template <int LOG2N, typename Tin, int SHIFT, bool GENERAL> int warp(const StftArgs&);
-//   template <int LOG2N, typename Tin, bool GENERAL>            int cta(const StftArgs&);
+//   template <int LOG2N, typename Tin, int SHIFT, int MODE> int warp(const StftArgs&);
+//   template <int LOG2N, typename Tin, int MODE>            int cta(const StftArgs&);
 #pragma once
 
 #include "b2s_host.hpp"
@@ -29,35 +29,35 @@ inline int sliding_shift(const StftArgs& a, int log2n) {
     return (s == 2 || s == 4 || s == 8 || s == 14) ? (int)s : 0;
 }
 
-template <int LOG2N, typename Tin, bool GENERAL, class Launcher>
+template <int LOG2N, typename Tin, int MODE, class Launcher>
 int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
     if constexpr (LOG2N >= 8 && sizeof(Tin) == 4) {
         switch (shift) {
-            case 2: return L.template warp<LOG2N, Tin, 2, GENERAL>(a);
-            case 4: return L.template warp<LOG2N, Tin, 4, GENERAL>(a);
-            case 8: return L.template warp<LOG2N, Tin, 8, GENERAL>(a);
-            case 14: return L.template warp<LOG2N, Tin, 14, GENERAL>(a);
+            case 2: return L.template warp<LOG2N, Tin, 2, MODE>(a);
+            case 4: return L.template warp<LOG2N, Tin, 4, MODE>(a);
+            case 8: return L.template warp<LOG2N, Tin, 8, MODE>(a);
+            case 14: return L.template warp<LOG2N, Tin, 14, MODE>(a);
             default: break;
         }
     }
-    return L.template warp<LOG2N, Tin, 0, GENERAL>(a);
+    return L.template warp<LOG2N, Tin, 0, MODE>(a);
 }
 
-template <typename Tin, bool GENERAL, class Launcher>
+template <typename Tin, int MODE, class Launcher>
 int dispatch_tg(const StftArgs& a, Launcher& L) {
     const int log2n = ilog2_exact(a.nperseg);
     const int shift = sliding_shift(a, log2n);
     switch (log2n) {
-        case 5: return dispatch_warp_shift<5, Tin, GENERAL>(a, L, shift);
-        case 6: return dispatch_warp_shift<6, Tin, GENERAL>(a, L, shift);
-        case 7: return dispatch_warp_shift<7, Tin, GENERAL>(a, L, shift);
-        case 8: return dispatch_warp_shift<8, Tin, GENERAL>(a, L, shift);
-        case 9: return dispatch_warp_shift<9, Tin, GENERAL>(a, L, shift);
-        case 10: return dispatch_warp_shift<10, Tin, GENERAL>(a, L, shift);
-        case 11: return L.template cta<11, Tin, GENERAL>(a);
-        case 12: return L.template cta<12, Tin, GENERAL>(a);
-        case 13: return L.template cta<13, Tin, GENERAL>(a);
-        case 14: return L.template cta<14, Tin, GENERAL>(a);
+        case 5: return dispatch_warp_shift<5, Tin, MODE>(a, L, shift);
+        case 6: return dispatch_warp_shift<6, Tin, MODE>(a, L, shift);
+        case 7: return dispatch_warp_shift<7, Tin, MODE>(a, L, shift);
+        case 8: return dispatch_warp_shift<8, Tin, MODE>(a, L, shift);
+        case 9: return dispatch_warp_shift<9, Tin, MODE>(a, L, shift);
+        case 10: return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
+        case 11: return L.template cta<11, Tin, MODE>(a);
+        case 12: return L.template cta<12, Tin, MODE>(a);
+        case 13: return L.template cta<13, Tin, MODE>(a);
+        case 14: return L.template cta<14, Tin, MODE>(a);
         default: return B2S_ERR_UNSUPPORTED;
     }
 }
@@ -66,8 +66,13 @@ template <class Launcher>
 int dispatch_stft(const StftArgs& a, Launcher& L) {
     // the reference's call (linear power, every bin) takes the branch-free epilogue
     const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
-    if (a.x_is_f64) return general ? dispatch_tg<double, true>(a, L) : dispatch_tg<double, false>(a, L);
-    return general ? dispatch_tg<float, true>(a, L) : dispatch_tg<float, false>(a, L);
+    const int mode = a.band_mode ? EPI_BAND : (general ? EPI_GENERAL : EPI_PLAIN);
+    if (a.x_is_f64) {
+        if (mode == EPI_BAND) return dispatch_tg<double, EPI_BAND>(a, L);
+        return mode == EPI_GENERAL ? dispatch_tg<double, EPI_GENERAL>(a, L) : dispatch_tg<double, EPI_PLAIN>(a, L);
+    }
+    if (mode == EPI_BAND) return dispatch_tg<float, EPI_BAND>(a, L);
+    return mode == EPI_GENERAL ? dispatch_tg<float, EPI_GENERAL>(a, L) : dispatch_tg<float, EPI_PLAIN>(a, L);
 }
 
 }  // namespace b2s

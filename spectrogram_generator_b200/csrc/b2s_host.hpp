@@ -9,6 +9,7 @@
 
 #include "../../include/b2s.h"
 #include "b2s_kernels.cuh"
+#include "b2s_dft_kernel.cuh"
 
 namespace b2s {
 
@@ -27,6 +28,7 @@ struct StftArgs {
     long long frame0, nframes;
     float* out;
     long long out_batch_stride;
+    int band_mode = 0;           // 1: out is [batch][nframes], the sum of bins kmin..kmax per frame
 };
 
 inline int ilog2_exact(int v) {
@@ -67,15 +69,24 @@ inline long long frames_available(long long n, int nperseg, int hop) {
 // except the device twiddle pointer).  `resident_groups` is how many frame
 // groups the launch can keep resident (grid * groups per CTA); it sizes the
 // work units so that every group gets several runs of consecutive frames.
-inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_groups, StftParams& p,
-                     std::string& err) {
-    const int log2n = ilog2_exact(a.nperseg);
+constexpr int kMaxNperseg = 16384;
+
+// 1: radix-16 FFT kernels (powers of two 32..16384); 2: direct-DFT kernel (everything
+// else up to 16384); 0: unsupported.
+inline int nperseg_support(int nperseg) {
+    if (nperseg < 1 || nperseg > kMaxNperseg) return 0;
+    const int l = ilog2_exact(nperseg);
+    return (l >= 5 && l <= 14) ? 1 : 2;
+}
+
+// Argument checks common to every kernel family (mirrors the shapes SciPy accepts).
+inline int validate_args(const StftArgs& a, std::string& err) {
     if (a.nperseg < 1 || a.hop < 1 || a.batch < 0 || a.nframes < 0 || a.n < 0) {
         err = "b2s: nperseg, hop must be >= 1 and sizes non-negative";
         return B2S_ERR_BAD_ARG;
     }
-    if (log2n < 5 || log2n > 14) {
-        err = "b2s: this entry handles power-of-two nperseg in [32, 16384]";
+    if (nperseg_support(a.nperseg) == 0) {
+        err = "b2s: nperseg must be in [1, 16384]";
         return B2S_ERR_UNSUPPORTED;
     }
     if (!a.x || !a.window || !a.out) {
@@ -96,10 +107,28 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
         return B2S_ERR_BAD_ARG;
     }
     const int kout = a.kmax - a.kmin + 1;
-    if (a.batch > 1 && (a.x_batch_stride < a.n || a.out_batch_stride < a.nframes * (long long)kout)) {
+    if (a.band_mode && a.out_mode != B2S_OUT_LINEAR) {
+        err = "b2s: band power is linear";
+        return B2S_ERR_BAD_ARG;
+    }
+    if (a.batch > 1 && (a.x_batch_stride < a.n || a.out_batch_stride < a.nframes * (long long)(a.band_mode ? 1 : kout))) {
         err = "b2s: batch strides overlap";
         return B2S_ERR_BAD_ARG;
     }
+    return B2S_OK;
+}
+
+inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_groups, StftParams& p,
+                     std::string& err) {
+    const int log2n = ilog2_exact(a.nperseg);
+    const int vrc = validate_args(a, err);
+    if (vrc != B2S_OK) return vrc;
+    if (log2n < 5 || log2n > 14) {
+        err = "b2s: the FFT kernels take power-of-two nperseg in [32, 16384]";
+        return B2S_ERR_UNSUPPORTED;
+    }
+    const int kout = a.kmax - a.kmin + 1;
+    (void)kout;
     p.x = a.x;
     p.x_batch_stride = a.x_batch_stride;
     p.frame0 = a.frame0;
@@ -156,5 +185,34 @@ inline void make_tables(int nperseg, std::vector<float>& out) {
 #define B2S_TBL(L) make_tables_t<L>(out)
     B2S_DISPATCH_LOG2N(log2n, B2S_TBL)
 #undef B2S_TBL
+}
+}  // namespace b2s
+
+namespace b2s {
+// W_N^j for the direct-DFT kernel
+inline void make_dft_table(int nperseg, std::vector<float>& out) {
+    out.assign(2 * (size_t)nperseg, 0.f);
+    for (int j = 0; j < nperseg; ++j) put_w(out, j, j, nperseg);
+}
+
+inline void fill_dft_params(const StftArgs& a, DftParams& p) {
+    p.x = a.x;
+    p.x_batch_stride = a.x_batch_stride;
+    p.frame0 = a.frame0;
+    p.out_batch_stride = a.out_batch_stride;
+    p.total_frames = a.batch * a.nframes;
+    p.window = a.window;
+    p.tw = nullptr;
+    p.out = a.out;
+    p.nframes = (int)a.nframes;
+    p.nperseg = a.nperseg;
+    p.hop = a.hop;
+    p.detrend = a.detrend ? 1 : 0;
+    p.out_mode = a.out_mode ? 1 : 0;
+    p.kmin = a.kmin;
+    p.kmax = a.kmax;
+    p.scale = (float)a.scale;
+    p.db_floor = a.db_floor;
+    p.band = a.band_mode;
 }
 }  // namespace b2s

@@ -62,7 +62,7 @@ struct Plan {
     static constexpr int TPT = (NS / 2) / G;                     // final tasks per thread
     static constexpr int BUF = M + (M >> 4) * 2;                 // padded complex slots
     static constexpr int RED = (G > 32) ? G / 32 : 1;            // mean partials per group
-    static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * 2 * RED * sizeof(float);
+    static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * 3 * RED * sizeof(float);
     // constant tables (complex entries, W = exp(-2 pi i ./.)), laid out so that
     // consecutive lanes read consecutive entries:
     //   P1  [15][16]    W_256^(r jm)           pass 1 (P >= 2)
@@ -105,25 +105,32 @@ template <> struct Loader<double> {
 };
 
 // ---- epilogue helpers ---------------------------------------------------------
-// GENERAL = false: linear power, all bins (the reference's call) -- no per-bin branches.
-template <bool GENERAL>
+// MODE 0: linear power, all bins (the reference's call) -- no per-bin branches.
+// MODE 1: general -- optional dB, bin crop [kmin, kmax].
+// MODE 2: band power -- nothing is stored per bin; the bins in [kmin, kmax] are summed
+//         per frame (PlotEngine._calculate_features, PlotEngine.py:238-239).
+enum : int { EPI_PLAIN = 0, EPI_GENERAL = 1, EPI_BAND = 2 };
+template <int MODE>
 struct Epi {
     float* row;        // out + frame row (already offset by -kmin)
     float s_edge;      // scale            (DC / Nyquist)
     float s_int;       // 2*scale          (interior bins)
     float floor;
+    float band = 0.f;  // MODE 2: this thread's partial band sum for the current frame
     int kmin, kmax, db;
     bool act = true;   // false: the group is past its last frame (warp kernel), stores are predicated off
-    B2S_DEVICE void put(int k, float p) const {
-        if constexpr (GENERAL) {
+    B2S_DEVICE void put(int k, float p) {
+        if constexpr (MODE == EPI_GENERAL) {
             if (db) p = 10.0f * log10f(fmaxf(p, floor));
             if (act && k >= kmin && k <= kmax) row[k] = p;
+        } else if constexpr (MODE == EPI_BAND) {
+            if (k >= kmin && k <= kmax) band += p;
         } else {
             if (act) row[k] = p;
         }
     }
     // Z[k] = zk, Z[M-k] = zm, w = W_N^k : interior bins k and M-k
-    B2S_DEVICE void pair(int k, int mk, float2 zk, float2 zm, float2 w) const {
+    B2S_DEVICE void pair(int k, int mk, float2 zk, float2 zm, float2 w) {
         const float ex = zk.x + zm.x, ey = zk.y - zm.y;      // 2E = zk + conj(zm)
         const float ox = zk.y + zm.y, oy = zm.x - zk.x;      // 2O = -i (zk - conj(zm))
         const float tx = fmaf(-oy, w.y, ox * w.x);           // T = w * 2O
@@ -133,8 +140,8 @@ struct Epi {
         put(k, 0.25f * s_int * fmaf(ax, ax, ay * ay));
         put(mk, 0.25f * s_int * fmaf(bx, bx, by * by));
     }
-    B2S_DEVICE void self_mid(int k, float2 z) const { put(k, s_int * fmaf(z.x, z.x, z.y * z.y)); }
-    B2S_DEVICE void dc_nyq(int M, float2 z0) const {
+    B2S_DEVICE void self_mid(int k, float2 z) { put(k, s_int * fmaf(z.x, z.x, z.y * z.y)); }
+    B2S_DEVICE void dc_nyq(int M, float2 z0) {
         const float a = z0.x + z0.y, b = z0.x - z0.y;
         put(0, s_edge * a * a);
         put(M, s_edge * b * b);
@@ -169,7 +176,7 @@ B2S_DEVICE float group_mean(const float2 (&v)[16], unsigned gmask, int grp, int 
 }
 
 // ---- the kernel ------------------------------------------------------------------
-template <int LOG2N, typename Tin, int MINB, bool GENERAL>
+template <int LOG2N, typename Tin, int MINB, int MODE>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const StftParams p) {
     using PL = Plan<LOG2N>;
     constexpr int M = PL::M, G = PL::G, NS = PL::NS, GF = PL::GF;
@@ -179,7 +186,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     const int grp = tid / G;
     const int j = tid - grp * G;
     float2* const buf = reinterpret_cast<float2*>(smem_raw) + (size_t)grp * PL::BUF;
-    float* const red = reinterpret_cast<float*>(smem_raw + (size_t)PL::FPC * PL::BUF * sizeof(float2)) + grp * 2 * PL::RED;
+    float* const red = reinterpret_cast<float*>(smem_raw + (size_t)PL::FPC * PL::BUF * sizeof(float2)) + grp * 3 * PL::RED;
     const unsigned lane = (unsigned)tid & 31u;
     const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(unsigned)(G - 1)));
 
@@ -189,7 +196,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     for (int r = 0; r < 16; ++r) win[r] = __ldg(reinterpret_cast<const float2*>(p.window) + (j + G * r));
 
     const int kout = p.kmax - p.kmin + 1;
-    Epi<GENERAL> epi;
+    Epi<MODE> epi;
     epi.s_edge = p.scale;
     epi.s_int = 2.0f * p.scale;
     epi.floor = p.db_floor;
@@ -321,6 +328,21 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
                     if constexpr (GF % 2 == 1) epi.self_mid(NS / 2 + ((GF - 1) / 2) * NS, V[(GF - 1) / 2]);
                 }
             }
+            if constexpr (MODE == EPI_BAND) {
+                // one number per frame: sum the partial band sums of the group (fixed order)
+                float bs = epi.band;
+                epi.band = 0.f;
+#pragma unroll
+                for (int o = (G < 32 ? G : 32) / 2; o >= 1; o >>= 1) bs += __shfl_xor_sync(gmask, bs, o);
+                if constexpr (G > 32) {
+                    if (lane == 0) red[2 * PL::RED + (j >> 5)] = bs;
+                    group_sync<G>(gmask, grp);
+                    bs = 0.f;
+#pragma unroll
+                    for (int w = 0; w < PL::RED; ++w) bs += red[2 * PL::RED + w];
+                }
+                if (j == 0) p.out[b * p.out_batch_stride + f] = bs;
+            }
         }
     }
 }
@@ -348,6 +370,56 @@ B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stri
     }
     for (; r < r1; ++r) { a0 += q[0]; q += in_stride; }
     out[(long long)slab * elems + e] = ((a0 + a1) + (a2 + a3)) * post_scale;
+}
+
+
+// ---- display scaling (PlotEngine._plot_spectrogram, PlotEngine.py:126-131) -----------------
+// Sxx_norm = clip(S / (base + 1e-20), 0, 1), base = max(S) unless a positive global_max is
+// given; with log_scale: 10*log10(Sxx_norm + 1e-12), nan_to_num, min-max to [0, 1] (zeros if
+// the dB range is <= 1e-6).  min/max of the dB image follow from min/max of S (monotone), so
+// one reduction pass + one elementwise pass suffice.  S >= 0, so float bits order like uints.
+B2S_GLOBAL void minmax_init_kernel(unsigned* mm) {
+    mm[0] = 0u;             // max
+    mm[1] = 0x7f800000u;    // min (+inf)
+}
+
+B2S_GLOBAL void minmax_kernel(const float* __restrict__ s, long long elems, unsigned* mm) {
+    float mx = 0.f, mn = __uint_as_float(0x7f800000u);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float v = fmaxf(s[i], 0.f);        // NaN / negative -> 0, like the reference's clip
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(mm, __float_as_uint(mx));
+        atomicMin(mm + 1, __float_as_uint(mn));
+    }
+}
+
+B2S_DEVICE float display_norm(float v, float inv_base) { return fminf(fmaxf(v * inv_base, 0.f), 1.f); }
+
+B2S_GLOBAL void display_scale_kernel(const float* __restrict__ s, long long elems, const unsigned* mm, int log_scale,
+                                     float global_max, float* __restrict__ out) {
+    const float base = (global_max > 0.f) ? global_max : __uint_as_float(mm[0]);
+    const float inv_base = 1.0f / (base + 1e-20f);
+    float lo = 0.f, inv_range = 0.f;
+    if (log_scale) {
+        const float hi = 10.0f * log10f(display_norm(__uint_as_float(mm[0]), inv_base) + 1e-12f);
+        lo = 10.0f * log10f(display_norm(__uint_as_float(mm[1]), inv_base) + 1e-12f);
+        inv_range = (hi - lo > 1e-6f) ? 1.0f / (hi - lo) : 0.f;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems;
+         i += (long long)gridDim.x * blockDim.x) {
+        float v = display_norm(s[i], inv_base);
+        if (log_scale) v = (10.0f * log10f(v + 1e-12f) - lo) * inv_range;
+        out[i] = v;
+    }
 }
 
 }  // namespace b2s

@@ -56,7 +56,7 @@ B2S_DEVICE float warp_group_mean(const float2 (&v)[16]) {
 //        2/4/8/14 = sliding register window, hop == SHIFT * nperseg / 16.
 // CREG: keep the window taps and the pass-1 twiddles of this thread in registers
 //       (they are the same for every frame) instead of re-reading them from shared memory.
-template <int LOG2N, typename Tin, int SHIFT, bool GENERAL, int NT = 256, int MINB = 2, bool CREG = false>
+template <int LOG2N, typename Tin, int SHIFT, int MODE, int NT = 256, int MINB = 2, bool CREG = false>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParams p) {
     using PL = Plan<LOG2N>;
     using WP = WarpPlan<LOG2N, NT>;
@@ -91,7 +91,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
     };
 
     const int kout = p.kmax - p.kmin + 1;
-    Epi<GENERAL> epi;
+    Epi<MODE> epi;
     epi.s_edge = p.scale;
     epi.s_int = 2.0f * p.scale;
     epi.floor = p.db_floor;
@@ -253,6 +253,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
                     }
                     if constexpr (GF % 2 == 1) epi.self_mid(NS / 2 + ((GF - 1) / 2) * NS, V[(GF - 1) / 2]);
                 }
+            }
+            if constexpr (MODE == EPI_BAND) {
+                float bs = epi.band;
+                epi.band = 0.f;
+#pragma unroll
+                for (int o = G / 2; o >= 1; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                if (j == 0 && act) p.out[b * p.out_batch_stride + f] = bs;
             }
         }
     }

@@ -50,6 +50,7 @@ class SpectrogramPath:
         self.last_f = None
         self.last_Sxx = None
         self.segment_map = []
+        self._last_Sxx_dev = None
 
     # -- the call at PlotEngine.py:113 / :232, with the band mask fused as a crop --
     def _spectrogram_cropped(self, data, fs, nperseg, fmin, fmax):
@@ -70,6 +71,7 @@ class SpectrogramPath:
         with torch.cuda.device(dev):
             xd = _to_device(x.reshape(1, -1), dev)
             Sd = eng.stft_psd(xd, plan, kmin=bins[0], kmax=bins[1])
+            self._last_Sxx_dev = Sd[0]                       # [frame][bin], kept for the display scaling
             S = _to_host(Sd[0], out_dtype)
         return f[bins[0]:bins[1] + 1], t, S.T
 
@@ -85,16 +87,12 @@ class SpectrogramPath:
         if Sxx.size == 0:
             self.last_t = np.array([])
             return None
-        base = np.max(Sxx) if global_max is None or global_max <= 0 else global_max
-        Sxx_norm = np.clip(Sxx / (base + 1e-20), 0.0, 1.0)
-        if log_scale:
-            eps = 1e-12
-            Sxx_db = 10.0 * np.log10(Sxx_norm + eps)
-            Sxx_db = np.nan_to_num(Sxx_db)
-            min_db, max_db = np.min(Sxx_db), np.max(Sxx_db)
-            Sxx_norm = (Sxx_db - min_db) / (max_db - min_db) if (max_db - min_db) > 1e-6 \
-                else np.zeros_like(Sxx_db)
-        return Sxx_norm
+        # display scaling (PlotEngine.py:126-131) on the device: global max/min reduction,
+        # clip, 10*log10(. + 1e-12), min-max -- the image comes back already normalised
+        dev_S = self._last_Sxx_dev
+        with torch.cuda.device(dev_S.device):
+            img = engine().display_scale(dev_S, bool(log_scale), global_max)
+            return _to_host(img, Sxx.dtype).T
 
     def plot_extra(self, signal_raw, signal_proc, fs, settings, global_max=None):
         """Source selection of PlotEngine.plot_extra (PlotEngine.py:95-105)."""
@@ -115,12 +113,28 @@ class SpectrogramPath:
         """PlotEngine.py:229-242."""
         fs = fs or self.last_fs
         settings = settings or self.last_settings
-        f, t, Sxx = self._spectrogram_cropped(signal, fs, settings["nperseg"], settings["fmin"],
-                                              settings["fmax"])
+        x, out_dtype, is_complex = _prepare_input(signal, -1)
+        if x.ndim != 1:
+            raise ValueError("the reference passes one 1-D sweep per call")
+        plan = triage(x.shape[-1], fs, ("tukey", .25), settings["nperseg"], None, None, "constant", True,
+                      "density", "psd", is_complex)
+        f = rfftfreq(plan.nperseg, fs)
+        t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
         if t.size == 0:
             return None, None
-        # an empty band mask gives sum over zero bins == 0 for every frame
-        power_feature = np.sum(Sxx, axis=0) if Sxx.shape[0] else np.zeros(t.shape, dtype=Sxx.dtype)
+        bins = band_to_bins(f, settings["fmin"], settings["fmax"])
+        if bins is None:
+            # an empty band mask gives a sum over zero bins == 0 for every frame
+            power_feature = np.zeros(t.shape, dtype=out_dtype)
+        else:
+            eng = engine()
+            eng.require_cuda()
+            dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None \
+                else torch.device(self.device)
+            with torch.cuda.device(dev):
+                # fused epilogue: only F numbers leave the kernel (no [F][K] spectrogram)
+                band = eng.band_power(_to_device(x.reshape(1, -1), dev), plan, bins[0], bins[1])
+                power_feature = _to_host(band[0], out_dtype)
         log_power = np.log10(power_feature + 1e-20)
         delta_log_power = np.diff(log_power, prepend=log_power[0])
         return t, np.column_stack([log_power, delta_log_power])

@@ -172,8 +172,7 @@ class Engine:
         support = lib.b2s_nperseg_support(plan.nperseg)
         if support == 0:
             raise NotImplementedError(
-                f"nperseg={plan.nperseg} is not supported by the B200 engine "
-                "(power-of-two 32..16384 on the fused kernel)")
+                f"nperseg={plan.nperseg} is not supported by the B200 engine (1..16384)")
         win = self.window_table(plan, x.device)
         fn = lib.b2s_stft_psd_f32 if x.dtype == torch.float32 else lib.b2s_stft_psd_f64
         with torch.cuda.device(x.device):
@@ -183,6 +182,46 @@ class Engine:
                     int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
                     nframes * kout, stream)
         _lib.check(rc, "b2s_stft_psd")
+        return out
+
+    def band_power(self, x: torch.Tensor, plan: Plan, kmin: int, kmax: int, *, frame0=0, nframes=None) -> torch.Tensor:
+        """Fused band-power feature: sum of bins kmin..kmax of every frame, CUDA float32
+        [B, nframes]; the spectrogram itself is never written (PlotEngine.py:238-239)."""
+        lib = _lib.load()
+        if x.dim() != 2 or not x.is_cuda or x.dtype not in (torch.float32, torch.float64):
+            raise ValueError("band_power expects a CUDA float32/float64 tensor of shape [batch, n]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        B, n = x.shape
+        if n != plan.n:
+            raise ValueError("plan was made for a different signal length")
+        nframes = plan.nframes - frame0 if nframes is None else int(nframes)
+        out = torch.empty((B, nframes), dtype=torch.float32, device=x.device)
+        if B == 0 or nframes == 0:
+            return out
+        if lib.b2s_nperseg_support(plan.nperseg) == 0:
+            raise NotImplementedError(f"nperseg={plan.nperseg} is not supported by the B200 engine (1..16384)")
+        win = self.window_table(plan, x.device)
+        fn = lib.b2s_stft_band_power_f32 if x.dtype == torch.float32 else lib.b2s_stft_band_power_f64
+        with torch.cuda.device(x.device):
+            rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
+                    plan.detrend, plan.scale, int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
+                    nframes, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_stft_band_power")
+        return out
+
+    def display_scale(self, s: torch.Tensor, log_scale: bool, global_max=None) -> torch.Tensor:
+        """PlotEngine.py:126-131 on the device; ``s`` is any contiguous CUDA float32 tensor."""
+        lib = _lib.load()
+        if not s.is_cuda or s.dtype != torch.float32 or not s.is_contiguous() or s.numel() == 0:
+            raise ValueError("display_scale expects a non-empty contiguous CUDA float32 tensor")
+        out = torch.empty_like(s)
+        scratch = torch.empty(2, dtype=torch.int32, device=s.device)
+        gm = float(global_max) if (global_max is not None and global_max > 0) else 0.0
+        with torch.cuda.device(s.device):
+            rc = lib.b2s_display_scale_f32(s.data_ptr(), s.numel(), int(bool(log_scale)), gm, out.data_ptr(),
+                                           scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_display_scale_f32")
         return out
 
     def batch_sum(self, s: torch.Tensor, post_scale: float = 1.0) -> torch.Tensor:

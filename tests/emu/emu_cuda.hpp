@@ -119,3 +119,18 @@ inline int __any_sync(unsigned mask, int pred) {
 
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
+
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline unsigned atomicMax(unsigned* a, unsigned v) {
+    std::lock_guard<std::mutex> g(emu::g_cta->mu);
+    const unsigned old = *a;
+    if (v > old) *a = v;
+    return old;
+}
+inline unsigned atomicMin(unsigned* a, unsigned v) {
+    std::lock_guard<std::mutex> g(emu::g_cta->mu);
+    const unsigned old = *a;
+    if (v < old) *a = v;
+    return old;
+}

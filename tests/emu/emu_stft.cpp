@@ -16,16 +16,16 @@ using namespace b2s;
 struct EmuLauncher {
     StftParams p;
     unsigned grid;
-    template <int LOG2N, typename Tin, int SHIFT, bool GENERAL>
+    template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs&) {
         using WP = WarpPlan<LOG2N>;
-        emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, GENERAL>(p); });
+        emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>(p); });
         return 0;
     }
-    template <int LOG2N, typename Tin, bool GENERAL>
+    template <int LOG2N, typename Tin, int MODE>
     int cta(const StftArgs&) {
         using PL = Plan<LOG2N>;
-        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, Tin, 1, GENERAL>(p); });
+        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, Tin, 1, MODE>(p); });
         return 0;
     }
 };
@@ -34,12 +34,25 @@ struct EmuLauncher {
 extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long long n, long long x_batch_stride,
                             int nperseg, int hop, const float* window, int detrend, double scale, int out_mode,
                             float db_floor, int kmin, int kmax, long long frame0, long long nframes, float* out,
-                            long long out_batch_stride, int grid, int force_chunk) {
+                            long long out_batch_stride, int grid, int force_chunk, int band_mode) {
     StftArgs a{x, x_is_f64, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, out_mode,
-               db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride};
+               db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, band_mode};
+    std::string err;
+    if (validate_args(a, err) < 0) return validate_args(a, err);
+    if (nperseg_support(nperseg) == 2) {
+        DftParams dp{};
+        fill_dft_params(a, dp);
+        std::vector<float> tw;
+        make_dft_table(nperseg, tw);
+        dp.tw = reinterpret_cast<const float2*>(tw.data());
+        if (dp.total_frames == 0) return 0;
+        const unsigned g = (unsigned)(dp.total_frames < grid ? dp.total_frames : grid);
+        if (x_is_f64) emu::launch(g, kDftThreads, dft_smem_bytes(nperseg), [&] { dft_psd_kernel<double>(dp); });
+        else emu::launch(g, kDftThreads, dft_smem_bytes(nperseg), [&] { dft_psd_kernel<float>(dp); });
+        return 0;
+    }
     EmuLauncher L;
     L.grid = (unsigned)grid;
-    std::string err;
     const int log2n = plan_stft(a, 1, (long long)grid * 4, L.p, err);
     if (log2n < 0) return log2n;
     if (force_chunk > 0) {

@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
 def test_host_only_entries():
     lib = _lib.load()
     assert lib.b2s_version() == 1
-    for n, want in [(32, 1), (512, 1), (16384, 1), (16, 0), (32768, 0)]:
+    for n, want in [(32, 1), (512, 1), (16384, 1), (16, 2), (1000, 2), (1, 2), (0, 0), (32768, 0)]:
         assert lib.b2s_nperseg_support(n) == want
     assert lib.b2s_frame_count(40000, 512, 128) == 309
     assert lib.b2s_frame_count(441000, 1024, 256) == 1719
@@ -52,9 +52,9 @@ def test_bad_arguments_are_reported_before_any_device_work():
     assert call(hop=0) == _lib.B2S_ERR_BAD_ARG
     assert call(nf=8) == _lib.B2S_ERR_BAD_ARG and b"frame range" in lib.b2s_last_error()
     assert call(kmax=129) == _lib.B2S_ERR_BAD_ARG
-    assert call(nperseg=100) == _lib.B2S_ERR_UNSUPPORTED
+    assert call(nperseg=40000) == _lib.B2S_ERR_UNSUPPORTED
     assert call(x=None) == _lib.B2S_ERR_BAD_ARG
     with pytest.raises(ValueError):
         _lib.check(call(kmin=5, kmax=4), "b2s_stft_psd_f32")
     with pytest.raises(NotImplementedError):
-        _lib.check(call(nperseg=100), "b2s_stft_psd_f32")
+        _lib.check(call(nperseg=40000), "b2s_stft_psd_f32")

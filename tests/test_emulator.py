@@ -148,3 +148,44 @@ def test_parseval_and_linearity(emu):
     np.testing.assert_allclose(lhs, energy, rtol=2e-6)
     S4 = emu.stft_psd(2.0 * x, plan)[0]
     np.testing.assert_array_equal(S4, 4.0 * emu.stft_psd(x, plan)[0])   # exact: power-of-two scaling
+
+
+@pytest.mark.parametrize("nperseg,hop", [(1000, 875), (96, 84), (100, 25), (33, 7), (8, 4), (1, 1), (250, 250)])
+def test_direct_dft_kernel_any_nperseg(emu, nperseg, hop):
+    """Lengths the radix-16 kernels do not take (GUI spin box: any integer 32..8192;
+    SciPy's clamp to len(x); SciPy's own tests use nperseg=8) run on the direct-DFT kernel."""
+    n = nperseg + hop * 6 + 3
+    x = signal(2, n, nperseg + hop, dc=1.5)
+    kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop)
+    plan = plan_for(n, 777.0, **kw)
+    got = emu.stft_psd(x, plan)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=777.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"dft nperseg={nperseg}")
+    if nperseg >= 8:
+        part = emu.stft_psd(x, plan, kmin=1, kmax=nperseg // 4, frame0=2, nframes=3)
+        assert np.array_equal(part, got[:, 2:5, 1:nperseg // 4 + 1])
+
+
+def test_direct_dft_known_answer_welch(emu):
+    """scipy/signal/tests/test_spectral.py:246-256 through the kernel (nperseg = 8)."""
+    x = np.zeros((1, 16), np.float32)
+    x[0, 0] = 1
+    x[0, 8] = 1
+    plan = plan_for(16, 1.0, window="hann", nperseg=8, noverlap=4)
+    S = emu.stft_psd(x, plan)[0]
+    q = np.array([0.08333333, 0.15277778, 0.22222222, 0.22222222, 0.11111111])
+    np.testing.assert_allclose(S.mean(axis=0), q, atol=1e-7, rtol=1e-6)
+
+
+@pytest.mark.parametrize("nperseg", [64, 512, 1024, 2048, 1000])
+def test_fused_band_power(emu, nperseg):
+    """Band-power epilogue == sum over the cropped spectrogram (PlotEngine.py:238-239)."""
+    n = nperseg * 5 + 17
+    x = signal(2, n, nperseg + 1, dc=0.5)
+    plan = plan_for(n, 1000.0, nperseg=nperseg)              # reference call: default overlap
+    kmin, kmax = 1, max(2, nperseg // 8)
+    full = emu.stft_psd(x, plan).astype(np.float64)
+    band = emu.band_power(x, plan, kmin, kmax)
+    np.testing.assert_allclose(band, full[:, :, kmin:kmax + 1].sum(axis=-1), rtol=2e-6)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=1000.0, nperseg=nperseg)
+    np.testing.assert_allclose(band, So[:, kmin:kmax + 1, :].sum(axis=1), rtol=1e-5)

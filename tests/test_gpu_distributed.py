@@ -1,0 +1,65 @@
+"""NCCL path on >= 2 GPUs of one box (skipped on a single-GPU box): sweeps sharded with
+the all-reduce for the mean, a long recording sharded by frame ranges, gather to rank 0."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import spectrogram_generator_b200 as sg
+        from spectrogram_generator_b200 import distributed as D, synth
+        from oracle import stft_oracle
+        x, kw = synth.config2(batch=37)
+        fs = kw.pop("fs")
+        lo, hi = D.shard_rows(37, world, rank)
+        f, t, mean, S_local = D.mean_spectrogram_sharded(x[lo:hi], 37, fs=fs, return_local=True, **kw)
+        _, _, mo = stft_oracle.mean_spectrogram(x.astype(np.float64), fs=fs, **kw)
+        assert np.max(np.abs(mean.cpu().numpy() - mo)) <= 1e-6 * mo.max()
+        counts = [D.shard_rows(37, world, r)[1] - D.shard_rows(37, world, r)[0] for r in range(world)]
+        allS = D.gather_slabs(S_local, counts, dst=0)
+        if rank == 0:
+            _, _, S1 = sg.spectrogram(x, fs=fs, **kw)
+            assert np.array_equal(np.moveaxis(allS.cpu().numpy(), -1, -2), S1), "sharded != single-GPU bits"
+        y, kw3 = synth.config3(n=48000 * 20)
+        fs3 = kw3.pop("fs")
+        plan = sg.triage(len(y), fs3, kw3["window"], kw3["nperseg"], kw3["noverlap"], None, "constant", True,
+                         "density", "psd")
+        f0, c = D.shard_frames(plan.nframes, world, rank)
+        slo, shi = D.sample_span(f0, c, plan.hop, plan.nperseg)
+        f, t_loc, S_loc, _ = D.spectrogram_time_sharded(y[slo:shi], len(y), fs=fs3, **kw3)
+        counts = [D.shard_frames(plan.nframes, world, r)[1] for r in range(world)]
+        full = D.gather_slabs(S_loc, counts, dst=0)
+        if rank == 0:
+            fw, tw, Sw = sg.spectrogram(y, fs=fs3, **kw3)
+            assert np.array_equal(full.cpu().numpy().T, Sw), "time-sharded != unsharded bits"
+        assert np.array_equal(t_loc, sg.windows.time_axis(len(y), 2048, 1536, fs3)[f0:f0 + c])
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on one box (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]

@@ -78,3 +78,35 @@ def test_plot_extra_source_selection_and_combine():
     assert path.spec_data_source is cat and np.array_equal(path.last_t, ref["last_t"])
     assert_parity(path.last_Sxx, ref["last_Sxx"])
     assert np.max(np.abs(img - ref["image"])) <= 1e-4
+
+
+def test_display_scale_kernel_matches_reference_lines():
+    import torch
+    rng = np.random.default_rng(11)
+    S = (rng.random((200, 37)) ** 8).astype(np.float32) * 3e-4
+    S[5, 5] = 0.0
+    eng = sg.engine()
+    Sd = torch.from_numpy(S).cuda()
+    for log_scale in (False, True):
+        for gmax in (None, 1e-4, 5.0):
+            want = stft_oracle.plot_postprocess(np.array([1.0]), np.array([0.0]), S.reshape(1, -1), 0.0, 2.0,
+                                                log_scale, gmax)["image"].reshape(S.shape)
+            got = eng.display_scale(Sd, log_scale, gmax).cpu().numpy()
+            assert np.max(np.abs(got - want)) <= 2e-6, (log_scale, gmax)
+    const = torch.full((10, 10), 0.25, device="cuda")
+    assert torch.equal(eng.display_scale(const, True), torch.zeros_like(const))      # dB range <= 1e-6 -> zeros
+    assert torch.equal(eng.display_scale(const, False), torch.ones_like(const))
+
+
+def test_band_power_entry_equals_cropped_sum():
+    import torch
+    x, fs = sweep(seed=5)
+    plan = sg.triage(len(x), fs, ("tukey", .25), 1024, None, None, "constant", True, "density", "psd")
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda().view(1, -1)
+    full = eng.stft_psd(xd, plan)
+    for kmin, kmax in [(0, 1), (0, 512), (3, 40), (512, 512)]:
+        band = eng.band_power(xd, plan, kmin, kmax)
+        torch.testing.assert_close(band, full[:, :, kmin:kmax + 1].sum(dim=-1), rtol=3e-6, atol=0)
+    part = eng.band_power(xd, plan, 3, 40, frame0=4, nframes=9)
+    assert torch.equal(part, eng.band_power(xd, plan, 3, 40)[:, 4:13])

@@ -295,11 +295,34 @@ def test_runs_on_the_callers_stream_and_device_api():
     assert torch.equal(eng.stft_psd(wide[:, :30000], plan), a)
 
 
-def test_non_power_of_two_is_loud():
-    if __import__("spectrogram_generator_b200")._lib.load().b2s_nperseg_support(1000):
-        pytest.skip("direct-DFT kernel present")
+@pytest.mark.parametrize("nperseg", [1000, 96, 160, 2000, 8000, 5, 31, 8191])
+def test_any_nperseg_direct_dft(nperseg):
+    """GUI.py:87-89 lets the user type any nperseg in 32..8192; SciPy clamps nperseg to
+    len(x).  Non-power-of-two lengths run on the direct-DFT kernel -- same bar."""
+    rng = np.random.default_rng(nperseg)
+    n = max(20000, 5 * nperseg)
+    t = np.arange(n) / 20000.0
+    x = (0.2 * rng.standard_normal((2, n)) + np.sin(2 * np.pi * 1234.0 * t) - 0.065).astype(np.float32)
+    f, tt, S = sg.spectrogram(x, fs=20000.0, nperseg=nperseg, scaling="density", mode="psd")
+    fr, tr, Sr = reference_path.reference_call(x.astype(np.float64), 20000.0, nperseg)
+    assert np.array_equal(f, fr) and np.array_equal(tt, tr)
+    assert_parity(S, Sr, what=f"dft nperseg={nperseg}", tail=big_tail(S))
+
+
+def test_nperseg_clamped_to_odd_length():
+    x = np.random.default_rng(1).standard_normal(777).astype(np.float32)
+    with pytest.warns(UserWarning, match="greater than input length"):
+        f, t, S = sg.spectrogram(x, fs=10.0, nperseg=1024)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fr, tr, Sr = reference_path.reference_call(x.astype(np.float64), 10.0, 1024)
+    assert np.array_equal(f, fr) and np.array_equal(t, tr) and S.shape == (389, 1)
+    assert_parity(S, Sr)
+
+
+def test_oversized_nperseg_is_loud():
     with pytest.raises(NotImplementedError):
-        sg.spectrogram(np.zeros(5000, np.float32), fs=1.0, nperseg=1000)
+        sg.spectrogram(np.zeros(100000, np.float32), fs=1.0, nperseg=20000)
 
 
 def test_matches_scipys_own_float32_accuracy():

@@ -24,7 +24,7 @@ def parity_report(S, So, floor=FLOOR):
     So = np.asarray(So, dtype=np.float64)
     assert S.shape == So.shape, (S.shape, So.shape)
     peak = So.max() if So.size else 0.0
-    big = So >= floor * peak
+    big = (So >= floor * peak) & (So > 0)
     d = np.abs(S - So)
     rel = float((d[big] / So[big]).max()) if big.any() else 0.0
     db = float(np.abs(10 * np.log10(np.maximum(S[big], 1e-300)) - 10 * np.log10(So[big])).max()) if big.any() else 0.0
@@ -42,7 +42,7 @@ def assert_parity(S, So, rel=REL_TOL, floor=FLOOR, abs_tol=ABS_TOL, db=DB_TOL, w
     assert r["abs"] <= abs_tol, f"{what}: abs err {r['abs']:.3e} * max > {abs_tol}"
     if tail > 0.0:
         S64, So64 = np.asarray(S, dtype=np.float64), np.asarray(So, dtype=np.float64)
-        big = So64 >= floor * So64.max()
+        big = (So64 >= floor * So64.max()) & (So64 > 0)
         relv = np.abs(S64[big] - So64[big]) / So64[big]
         frac = float(np.mean(relv > rel))
         r["tail_frac"] = frac
@@ -77,7 +77,7 @@ class Emulator:
         self.lib.emu_stft_psd.argtypes = [c.c_void_p, c.c_int, c.c_longlong, c.c_longlong, c.c_longlong,
                                           c.c_int, c.c_int, c.c_void_p, c.c_int, c.c_double, c.c_int,
                                           c.c_float, c.c_int, c.c_int, c.c_longlong, c.c_longlong,
-                                          c.c_void_p, c.c_longlong, c.c_int, c.c_int]
+                                          c.c_void_p, c.c_longlong, c.c_int, c.c_int, c.c_int]
         self.lib.emu_batch_sum.restype = c.c_int
         self.lib.emu_batch_sum.argtypes = [c.c_void_p, c.c_longlong, c.c_int, c.c_int, c.c_longlong,
                                            c.c_void_p, c.c_float]
@@ -94,7 +94,19 @@ class Emulator:
         out = np.full((B, nframes, kout), np.nan, np.float32)
         rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
                                    plan.hop, w.ctypes.data, plan.detrend, plan.scale, out_mode, db_floor,
-                                   kmin, kmax, frame0, nframes, out.ctypes.data, nframes * kout, grid, chunk)
+                                   kmin, kmax, frame0, nframes, out.ctypes.data, nframes * kout, grid, chunk, 0)
+        assert rc == 0, rc
+        return out
+
+    def band_power(self, x2d, plan, kmin, kmax, frame0=0, nframes=None, grid=2, chunk=0):
+        x2d = np.ascontiguousarray(x2d)
+        B, n = x2d.shape
+        nframes = plan.nframes - frame0 if nframes is None else nframes
+        w = plan.win64.astype(np.float32)
+        out = np.full((B, nframes), np.nan, np.float32)
+        rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
+                                   plan.hop, w.ctypes.data, plan.detrend, plan.scale, 0, 0.0,
+                                   kmin, kmax, frame0, nframes, out.ctypes.data, nframes, grid, chunk, 1)
         assert rc == 0, rc
         return out
 
