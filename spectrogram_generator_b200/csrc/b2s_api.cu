@@ -84,7 +84,8 @@ std::map<const void*, KernelState> g_kern;     // guarded by g_mu
 
 // One launch of an STFT kernel (either family): persistent grid sized from the
 // occupancy, work units sized from the grid (b2s::plan_stft).
-int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream) {
+int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
+               bool direct_table = false) {
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
@@ -111,7 +112,7 @@ int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftAr
     rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
-    rc = twiddles(dev, a.nperseg, false, &p.tw);
+    rc = twiddles(dev, a.nperseg, direct_table, &p.tw);
     if (rc != B2S_OK) return rc;
     // persistent grid: never more CTAs than work
     const long long need = (p.n_units + fpc - 1) / fpc;
@@ -157,32 +158,24 @@ int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
 
 struct CudaLauncher {
     cudaStream_t stream;
+    bool allow_pair = false;     // frame-pair kernel: measured slower than the warp kernel so far (opt-in)
+    template <int LOG2N, int S, int MODE>
+    int pair(const b2s::StftArgs& a) {
+        using PP = b2s::PairPlan<LOG2N>;
+        return launch_any((const void*)b2s::stft_psd_pair_kernel<LOG2N, S, MODE>, PP::NT, PP::SMEM, PP::FPC, a,
+                          stream, true);
+    }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const b2s::StftArgs& a) {
         using WP = b2s::WarpPlan<LOG2N>;
 #ifdef B2S_EXPERIMENTS
-        // A/B variants for tuning runs (tools/microbench.py --variant): selected by B2S_VARIANT
-        if constexpr ((LOG2N == 9 || LOG2N == 10) && SHIFT == 4 && !GENERAL && sizeof(Tin) == 4) {
+        // A/B variants for tuning runs (B2S_VARIANT=n python tools/microbench.py ...)
+        if constexpr ((LOG2N == 9 || LOG2N == 10) && SHIFT == 4 && MODE == 0 && sizeof(Tin) == 4) {
             const char* v = getenv("B2S_VARIANT");
             const int vi = v ? atoi(v) : 0;
-            if (vi == 1) {
-                using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 3, true>,
-                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
-            }
-            if (vi == 2) {
-                using W2 = b2s::WarpPlan<LOG2N, 256>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 256, 1, true>,
-                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
-            }
             if (vi == 3) {
                 using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 4, false>,
-                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
-            }
-            if (vi == 4) {
-                using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 2, true>,
+                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 4>,
                                   W2::NT, W2::SMEM, W2::FPC, a, stream);
             }
         }
@@ -214,6 +207,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     }
     if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
     CudaLauncher L{(cudaStream_t)stream};
+    if (const char* v = getenv("B2S_PAIR")) L.allow_pair = (atoi(v) != 0);
     return b2s::dispatch_stft(a, L);
 }
 

@@ -19,6 +19,7 @@
 #define B2S_LAUNCH_BOUNDS(a, b)
 #define B2S_DYN_SMEM(name) unsigned char* const name = emu::dyn_smem()
 #define B2S_DYN_SMEM_F2(name) float2* const name = reinterpret_cast<float2*>(emu::dyn_smem())
+#define B2S_DYN_SMEM_F4(name) float4* const name = reinterpret_cast<float4*>(emu::dyn_smem())
 #else
 #define B2S_HD __host__ __device__ __forceinline__
 #define B2S_DEVICE __device__ __forceinline__
@@ -26,6 +27,7 @@
 #define B2S_LAUNCH_BOUNDS(a, b) __launch_bounds__(a, b)
 #define B2S_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define B2S_DYN_SMEM_F2(name) extern __shared__ __align__(16) float2 name[]
+#define B2S_DYN_SMEM_F4(name) extern __shared__ __align__(16) float4 name[]
 // named barrier over `n` threads (n a multiple of 32), id 1..15
 __device__ __forceinline__ void b2s_bar_sync(int id, int n) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
@@ -35,8 +37,18 @@ __device__ __forceinline__ void b2s_bar_sync(int id, int n) {
 namespace b2s {
 
 B2S_HD float2 cmk(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+// Complex add / subtract.  On sm_100a these are single packed FADD2 instructions (two fp32
+// adds per issue slot, IEEE round-to-nearest like the scalar form -- results are identical).
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+B2S_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+B2S_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, cmk(-b.x, -b.y)); }
+// a + s * b with s = (sx, sy) a compile-time sign pattern
+B2S_HD float2 cfma_sign(float2 b, float sx, float sy, float2 a) { return __ffma2_rn(b, cmk(sx, sy), a); }
+#else
 B2S_HD float2 cadd(float2 a, float2 b) { return cmk(a.x + b.x, a.y + b.y); }
 B2S_HD float2 csub(float2 a, float2 b) { return cmk(a.x - b.x, a.y - b.y); }
+B2S_HD float2 cfma_sign(float2 b, float sx, float sy, float2 a) { return cmk(fmaf(b.x, sx, a.x), fmaf(b.y, sy, a.y)); }
+#endif
 // (a.x + i a.y) * (w.x + i w.y): 2 mul + 2 fma
 B2S_HD float2 cmul(float2 a, float2 w) {
     return cmk(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));

@@ -154,6 +154,7 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     long long cf = (want_units > 0) ? (total + want_units - 1) / want_units : a.nframes;
     if (cf < 1) cf = 1;
     if (cf > 64) cf = 64;
+    if (cf > 1 && (cf & 1)) ++cf;          // the frame-pair kernel walks a run two frames at a time
     if (cf > a.nframes) cf = a.nframes > 0 ? a.nframes : 1;
     p.chunk_frames = (int)cf;
     p.units_per_signal = (a.nframes + cf - 1) / cf;

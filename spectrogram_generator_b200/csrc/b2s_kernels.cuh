@@ -131,14 +131,13 @@ struct Epi {
     }
     // Z[k] = zk, Z[M-k] = zm, w = W_N^k : interior bins k and M-k
     B2S_DEVICE void pair(int k, int mk, float2 zk, float2 zm, float2 w) {
-        const float ex = zk.x + zm.x, ey = zk.y - zm.y;      // 2E = zk + conj(zm)
-        const float ox = zk.y + zm.y, oy = zm.x - zk.x;      // 2O = -i (zk - conj(zm))
-        const float tx = fmaf(-oy, w.y, ox * w.x);           // T = w * 2O
-        const float ty = fmaf(oy, w.x, ox * w.y);
-        const float ax = ex + tx, ay = ey + ty;              // 2 X[k]
-        const float bx = ex - tx, by = ey - ty;              // 2 conj(X[M-k])
-        put(k, 0.25f * s_int * fmaf(ax, ax, ay * ay));
-        put(mk, 0.25f * s_int * fmaf(bx, bx, by * by));
+        const float2 e = cfma_sign(zm, 1.f, -1.f, zk);                           // 2E = zk + conj(zm)
+        const float2 o = cfma_sign(cmk(zk.y, zk.x), 1.f, -1.f, cmk(zm.y, zm.x)); // 2O = -i (zk - conj(zm))
+        const float2 t = cmul(o, w);                                             // T = w * 2O
+        const float2 a = cadd(e, t);                                             // 2 X[k]
+        const float2 bq = csub(e, t);                                            // 2 conj(X[M-k])
+        put(k, 0.25f * s_int * fmaf(a.x, a.x, a.y * a.y));
+        put(mk, 0.25f * s_int * fmaf(bq.x, bq.x, bq.y * bq.y));
     }
     B2S_DEVICE void self_mid(int k, float2 z) { put(k, s_int * fmaf(z.x, z.x, z.y * z.y)); }
     B2S_DEVICE void dc_nyq(int M, float2 z0) {

@@ -52,11 +52,58 @@ B2S_DEVICE float warp_group_mean(const float2 (&v)[16]) {
     return tot * (1.0f / (float)(32 * G));
 }
 
+// Front half of a frame for the warp kernel: detrend + window from the raw samples in
+// `cur` into `v`, then slide `cur` to the next frame and issue its new loads.
+// ROT rotates the register names instead of moving data: logical sample r of the current
+// frame lives in cur[(r + ROT) & 15]; sliding by SHIFT is then just ROT += SHIFT for the
+// next frame (the caller switches over the reachable ROT values), and the SHIFT new loads
+// land in the slots the oldest samples occupied.
+template <int LOG2N, typename Tin, int SHIFT, int ROT>
+B2S_DEVICE void warp_front(float2 (&cur)[16], float2 (&v)[16], const float2* wtaps, int detrend, bool do_next,
+                           const Tin* xn, int j, int vec_ok) {
+    constexpr int G = Plan<LOG2N>::G;
+    if (detrend) {
+        const float m1 = warp_group_mean<G>(cur);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = cmk(cur[(r + ROT) & 15].x - m1, cur[(r + ROT) & 15].y - m1);
+        const float nr = -warp_group_mean<G>(v);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float2 w = wtaps[G * r];
+            v[r].x = fmaf(v[r].x, w.x, nr * w.x);
+            v[r].y = fmaf(v[r].y, w.y, nr * w.y);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float2 w = wtaps[G * r];
+            v[r] = cmk(cur[(r + ROT) & 15].x * w.x, cur[(r + ROT) & 15].y * w.y);
+        }
+    }
+    if (do_next) {
+        if constexpr (SHIFT != 0) {
+            // logical r' = 16-SHIFT+i of the next frame -> physical slot (i + ROT) & 15
+#pragma unroll
+            for (int i = 0; i < SHIFT; ++i)
+                cur[(i + ROT) & 15] = Loader<Tin>::ld2(xn + 2 * (j + G * (16 - SHIFT + i)));
+        } else if (vec_ok) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) cur[r] = Loader<Tin>::ld2(xn + 2 * (j + G * r));
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const Tin* q = xn + 2 * (j + G * r);
+                cur[r] = cmk(Loader<Tin>::ld1(q), Loader<Tin>::ld1(q + 1));
+            }
+        }
+    }
+}
+
 // SHIFT: 0 = reload the whole frame every time (any hop; scalar loads when !vec_ok),
 //        2/4/8/14 = sliding register window, hop == SHIFT * nperseg / 16.
-// CREG: keep the window taps and the pass-1 twiddles of this thread in registers
-//       (they are the same for every frame) instead of re-reading them from shared memory.
-template <int LOG2N, typename Tin, int SHIFT, int MODE, int NT = 256, int MINB = 2, bool CREG = false>
+// (Keeping the window taps / pass-1 twiddles in registers was measured and lost: at 168-225
+//  registers per thread the occupancy drop costs more than the 39 LDS per frame it saves.)
+template <int LOG2N, typename Tin, int SHIFT, int MODE, int NT = 256, int MINB = 2>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParams p) {
     using PL = Plan<LOG2N>;
     using WP = WarpPlan<LOG2N, NT>;
@@ -75,20 +122,6 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
         for (int i = tid; i < PL::TABLE; i += WP::NT) sm[WP::OFF_TAB + i] = __ldg(p.tw + i);
     }
     __syncthreads();
-
-    float2 wreg[CREG ? 16 : 1], treg[CREG ? 16 : 1];
-    if constexpr (CREG) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) wreg[r] = sm[WP::OFF_WIN + j + G * r];
-        if constexpr (PL::P == 2) {
-#pragma unroll
-            for (int r = 1; r < 16; ++r) treg[r] = sm[WP::OFF_TAB + PL::OFF_P1 + (r - 1) * 16 + (j & 15)];
-        }
-    }
-    auto wtap = [&](int r) -> float2 {
-        if constexpr (CREG) return wreg[r];
-        else return sm[WP::OFF_WIN + j + G * r];
-    };
 
     const int kout = p.kmax - p.kmin + 1;
     Epi<MODE> epi;
@@ -128,51 +161,38 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
             }
         }
 
+        int rot = 0;          // warp-uniform register rotation of `cur` (see warp_front)
         for (int f = f_begin;; ++f) {
             const bool act = uvalid && (f < f_end);
             if (!__any_sync(0xffffffffu, act)) break;
             epi.act = act;
             epi.row = ob + (long long)f * kout;
 
-            // ---- detrend (two fp32 passes, see stft_psd_kernel) + window ----
+            // ---- detrend + window -> v; slide / prefetch the next frame's samples ----
             float2 v[16];
-            if (p.detrend) {
-                const float m1 = warp_group_mean<G>(cur);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) v[r] = cmk(cur[r].x - m1, cur[r].y - m1);
-                const float nr = -warp_group_mean<G>(v);
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float2 w = wtap(r);
-                    v[r].x = fmaf(v[r].x, w.x, nr * w.x);
-                    v[r].y = fmaf(v[r].y, w.y, nr * w.y);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const float2 w = wtap(r);
-                    v[r] = cmk(cur[r].x * w.x, cur[r].y * w.y);
-                }
-            }
-
-            // ---- next frame's samples: slide the register window, prefetch the new tail ----
-            if (act && f + 1 < f_end) {
+            {
+                const bool do_next = act && (f + 1 < f_end);
                 const Tin* const xn = xb + (long long)(f + 1) * p.hop;
-                if constexpr (SHIFT != 0) {
-#pragma unroll
-                    for (int r = 0; r < 16 - SHIFT; ++r) cur[r] = cur[r + SHIFT];
-#pragma unroll
-                    for (int r = 16 - SHIFT; r < 16; ++r) cur[r] = Loader<Tin>::ld2(xn + 2 * (j + G * r));
-                } else if (p.vec_ok) {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) cur[r] = Loader<Tin>::ld2(xn + 2 * (j + G * r));
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const Tin* q = xn + 2 * (j + G * r);
-                        cur[r] = cmk(Loader<Tin>::ld1(q), Loader<Tin>::ld1(q + 1));
-                    }
+                const float2* const wt = &sm[WP::OFF_WIN + j];
+                constexpr int STEP = (SHIFT == 0) ? 16 : ((SHIFT % 4 == 0) ? ((SHIFT % 8 == 0) ? 8 : 4) : 2);
+                switch (rot) {
+#define B2S_FRONT_CASE(R)                                                                                   \
+    case R:                                                                                                 \
+        if constexpr ((R) % STEP == 0)                                                                      \
+            warp_front<LOG2N, Tin, SHIFT, (R)>(cur, v, wt, p.detrend, do_next, xn, j, p.vec_ok);            \
+        break;
+                    B2S_FRONT_CASE(0)
+                    B2S_FRONT_CASE(2)
+                    B2S_FRONT_CASE(4)
+                    B2S_FRONT_CASE(6)
+                    B2S_FRONT_CASE(8)
+                    B2S_FRONT_CASE(10)
+                    B2S_FRONT_CASE(12)
+                    B2S_FRONT_CASE(14)
+#undef B2S_FRONT_CASE
+                    default: break;
                 }
+                rot = (rot + SHIFT) & 15;
             }
 
             // ---- pass 0: radix-16 over r (stride G), Ns 1 -> 16 ----
@@ -194,10 +214,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
 #pragma unroll
                 for (int r = 0; r < 16; ++r) v[r] = sm[bufo + phys(j + r * G)];
 #pragma unroll
-                for (int r = 1; r < 16; ++r) {
-                    if constexpr (CREG) v[r] = cmul(v[r], treg[r]);
-                    else v[r] = cmul(v[r], sm[WP::OFF_TAB + PL::OFF_P1 + (r - 1) * 16 + jm]);
-                }
+                for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], sm[WP::OFF_TAB + PL::OFF_P1 + (r - 1) * 16 + jm]);
                 radix16(v);
                 __syncwarp();
                 const int base = (j - jm) * 16 + jm;

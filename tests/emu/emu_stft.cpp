@@ -2,6 +2,7 @@
 // Build: g++ -std=c++20 -O1 -DB2S_EMU -shared -fPIC -pthread -I tests/emu \
 //        -I spectrogram_generator_b200/csrc tests/emu/emu_stft.cpp -o tests/emu/libb2s_emu.so
 #include "emu_cuda.hpp"
+#include <cstdlib>
 
 thread_local uint3_ threadIdx;
 thread_local uint3_ blockIdx;
@@ -16,6 +17,17 @@ using namespace b2s;
 struct EmuLauncher {
     StftParams p;
     unsigned grid;
+    bool allow_pair = true;
+    std::vector<float> direct;
+    template <int LOG2N, int S, int MODE>
+    int pair(const StftArgs& a) {
+        using PP = PairPlan<LOG2N>;
+        make_dft_table(a.nperseg, direct);
+        StftParams q = p;
+        q.tw = reinterpret_cast<const float2*>(direct.data());
+        emu::launch(grid, PP::NT, PP::SMEM, [&] { stft_psd_pair_kernel<LOG2N, S, MODE>(q); });
+        return 0;
+    }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs&) {
         using WP = WarpPlan<LOG2N>;
@@ -64,6 +76,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     make_tables(nperseg, tw);
     L.p.tw = reinterpret_cast<const float2*>(tw.data());
     if (L.p.n_units == 0) return 0;
+    if (const char* v = getenv("B2S_NO_PAIR")) L.allow_pair = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
 
