@@ -158,12 +158,11 @@ int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
 
 struct CudaLauncher {
     cudaStream_t stream;
-    bool allow_pair = false;     // frame-pair kernel: measured slower than the warp kernel so far (opt-in)
-    template <int LOG2N, int S, int MODE>
-    int pair(const b2s::StftArgs& a) {
-        using PP = b2s::PairPlan<LOG2N>;
-        return launch_any((const void*)b2s::stft_psd_pair_kernel<LOG2N, S, MODE>, PP::NT, PP::SMEM, PP::FPC, a,
-                          stream, true);
+    bool allow_duo = true;
+    template <typename Tin, int S, int MODE>
+    int duo(const b2s::StftArgs& a) {
+        using DP = b2s::DuoPlan;
+        return launch_any((const void*)b2s::stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const b2s::StftArgs& a) {
@@ -207,7 +206,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     }
     if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
     CudaLauncher L{(cudaStream_t)stream};
-    if (const char* v = getenv("B2S_PAIR")) L.allow_pair = (atoi(v) != 0);
+    if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     return b2s::dispatch_stft(a, L);
 }
 

@@ -8,12 +8,15 @@
 // A Launcher provides
 //   template <int LOG2N, typename Tin, int SHIFT, int MODE> int warp(const StftArgs&);
 //   template <int LOG2N, typename Tin, int MODE>            int cta(const StftArgs&);
-//   template <int LOG2N, int S, int MODE>                   int pair(const StftArgs&);
-//   bool allow_pair;
+//   template <typename Tin, int S, int MODE>                int duo(const StftArgs&);
+//   bool allow_duo;
+//
+//   nperseg == 512 with hop in {64, 128, 256} (2-element aligned frames) takes the packed
+//   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh).
 #pragma once
 
 #include "b2s_host.hpp"
-#include "b2s_pair_kernel.cuh"
+#include "b2s_duo_kernel.cuh"
 #include "b2s_warp_kernel.cuh"
 
 namespace b2s {
@@ -32,31 +35,27 @@ inline int sliding_shift(const StftArgs& a, int log2n) {
     return (s == 2 || s == 4 || s == 8 || s == 14) ? (int)s : 0;
 }
 
-// frame-pair kernel: nperseg 256 / 512, float samples, hop = S * nperseg/8
-inline int pair_slots(const StftArgs& a, int log2n) {
-    if (a.x_is_f64 || (log2n != 8 && log2n != 9) || !frames_vec_aligned(a)) return 0;
-    const long long n8 = a.nperseg / 8;
-    if (a.hop % n8) return 0;
-    const long long s = a.hop / n8;
-    return (s == 1 || s == 2 || s == 4 || s == 7 || s == 8) ? (int)s : 0;
+// frame-duo kernel: nperseg 512, hop = S * 32 samples, S in {2, 4, 8}
+inline int duo_slots(const StftArgs& a, int log2n) {
+    if (log2n != 9 || !frames_vec_aligned(a) || a.hop % 32) return 0;
+    const long long s = a.hop / 32;
+    return (s == 2 || s == 4 || s == 8) ? (int)s : 0;
 }
 
-template <int LOG2N, int MODE, class Launcher>
-int dispatch_pair(const StftArgs& a, Launcher& L, int s) {
+template <typename Tin, int MODE, class Launcher>
+int dispatch_duo(const StftArgs& a, Launcher& L, int s) {
     switch (s) {
-        case 1: return L.template pair<LOG2N, 1, MODE>(a);
-        case 2: return L.template pair<LOG2N, 2, MODE>(a);
-        case 4: return L.template pair<LOG2N, 4, MODE>(a);
-        case 7: return L.template pair<LOG2N, 7, MODE>(a);
-        default: return L.template pair<LOG2N, 8, MODE>(a);
+        case 2: return L.template duo<Tin, 2, MODE>(a);
+        case 4: return L.template duo<Tin, 4, MODE>(a);
+        default: return L.template duo<Tin, 8, MODE>(a);
     }
 }
 
 template <int LOG2N, typename Tin, int MODE, class Launcher>
 int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
-    if constexpr ((LOG2N == 8 || LOG2N == 9) && sizeof(Tin) == 4) {
-        const int s = L.allow_pair ? pair_slots(a, LOG2N) : 0;
-        if (s) return dispatch_pair<LOG2N, MODE>(a, L, s);
+    if constexpr (LOG2N == 9) {
+        const int s = L.allow_duo ? duo_slots(a, LOG2N) : 0;
+        if (s) return dispatch_duo<Tin, MODE>(a, L, s);
     }
     if constexpr (LOG2N >= 8 && sizeof(Tin) == 4) {
         switch (shift) {

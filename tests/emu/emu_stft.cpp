@@ -17,15 +17,11 @@ using namespace b2s;
 struct EmuLauncher {
     StftParams p;
     unsigned grid;
-    bool allow_pair = true;
-    std::vector<float> direct;
-    template <int LOG2N, int S, int MODE>
-    int pair(const StftArgs& a) {
-        using PP = PairPlan<LOG2N>;
-        make_dft_table(a.nperseg, direct);
-        StftParams q = p;
-        q.tw = reinterpret_cast<const float2*>(direct.data());
-        emu::launch(grid, PP::NT, PP::SMEM, [&] { stft_psd_pair_kernel<LOG2N, S, MODE>(q); });
+    bool allow_duo = true;
+    template <typename Tin, int S, int MODE>
+    int duo(const StftArgs&) {
+        using DP = DuoPlan;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_kernel<Tin, S, MODE>(p); });
         return 0;
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
@@ -76,7 +72,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     make_tables(nperseg, tw);
     L.p.tw = reinterpret_cast<const float2*>(tw.data());
     if (L.p.n_units == 0) return 0;
-    if (const char* v = getenv("B2S_NO_PAIR")) L.allow_pair = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
 
