@@ -256,7 +256,7 @@ def run_gpu(args):
                        "frames_per_sweep": F, "bins": K,
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only"},
-            "roofline": {"bound": "hbm", "kernel": "stft_psd_warp_kernel<9,float,SHIFT=4>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, packed fp32x2)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel_ms": kern_ms, "frac_of_nominal_8000": achieved / 8000.0},

@@ -96,47 +96,92 @@ struct DuoPlan {
     static constexpr int FPC = NT / G;                   // duos in flight per CTA
     static constexpr int ROW = 17;                       // float4 slots per lane row (16 + 1 pad)
     static constexpr int BUF = 16 * ROW;                 // exchange buffer of one duo, float4 units
-    // shared memory: float2 tables, then the float4 exchange buffers
-    static constexpr int OFF_WIN = 0;                    // [256]    window taps (w[2n], w[2n+1]) * sqrt(scale/2)
-    static constexpr int OFF_TW1 = OFF_WIN + M;          // [15][16] W_256^(t q)
-    static constexpr int OFF_TWP = OFF_TW1 + 15 * 16;    // [8][16]  W_512^(q + 16 p)
-    static constexpr int TAB = OFF_TWP + 8 * 16;         // float2 units (a multiple of 2)
-    static constexpr size_t SMEM = (size_t)TAB * sizeof(float2) + (size_t)FPC * BUF * sizeof(float4);
-    static_assert(TAB % 2 == 0, "exchange buffers are 16-byte aligned");
+    // shared memory, float4 units.  Every constant table is [j][lane] with the entries for the
+    // two consecutive indices 2j, 2j+1 in one float4, so one LDS.128 fetches two of them and the
+    // 16 lanes of a duo read 256 consecutive bytes (both duos of a warp read the same ones).
+    static constexpr int OFF_WIN = 0;                    // [8][16] window taps of slots 2j, 2j+1, * sqrt(scale/2)
+    static constexpr int OFF_TW1 = OFF_WIN + 8 * 16;     // [8][16] W_256^(t' q), t' = 2j, 2j+1
+    static constexpr int OFF_TWP = OFF_TW1 + 8 * 16;     // [4][16] W_512^(q + 16 p), p = 2j, 2j+1
+    static constexpr int TAB = OFF_TWP + 4 * 16;
+    static constexpr size_t SMEM = (size_t)(TAB + FPC * BUF) * sizeof(float4);
 };
 
+// Coarse per-frame means of the duo (the detrend pivots), from per-slot sums added in a
+// fixed frame-relative order: blocks of S slots first (frames A and B share 16/S - 1 blocks).
+template <int S>
+B2S_DEVICE void duo_coarse_means(const float2 (&cur)[16 + S], float& cA, float& cB) {
+    constexpr int NB = 16 / S;
+    float blk[NB + 1];
+#pragma unroll
+    for (int bi = 0; bi <= NB; ++bi) {
+        float ss[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
+#pragma unroll
+        for (int w = S / 2; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
+        blk[bi] = ss[0];
+    }
+    if constexpr (NB == 2) {
+        cA = blk[0] + blk[1];
+        cB = blk[1] + blk[2];
+    } else if constexpr (NB == 4) {
+        cA = (blk[0] + blk[1]) + (blk[2] + blk[3]);
+        cB = (blk[1] + blk[2]) + (blk[3] + blk[4]);
+    } else {
+        cA = ((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7]));
+        cB = ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8]));
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        cA += __shfl_xor_sync(0xffffffffu, cA, o);
+        cB += __shfl_xor_sync(0xffffffffu, cB, o);
+    }
+    cA *= 1.0f / 512.0f;
+    cB *= 1.0f / 512.0f;
+}
+
 // S = hop / 32: raw complex slots the frame start advances per frame
-template <typename Tin, int S, int MODE>
-B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kernel(const StftParams p) {
+template <typename Tin, int S, int MODE, int MINB = DuoPlan::MINB, int OPT = 0>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const StftParams p) {
     using DP = DuoPlan;
+    // timing ablations (tools/ubench/duo_bench only; results are wrong with any of these set)
+    constexpr bool ABL_NOSTG = (OPT & 8) != 0, ABL_NOXCHG = (OPT & 16) != 0, ABL_NOSHFL = (OPT & 32) != 0;
     using PL = Plan<9>;
     constexpr int M = DP::M, G = DP::G, ROW = DP::ROW;
     constexpr int NCUR = 16 + S;                         // raw complex slots of the duo
     constexpr int KEEP = (NCUR > 2 * S) ? NCUR - 2 * S : 0;   // slots shared with the next duo
 
-    B2S_DYN_SMEM(smem_raw);
-    float2* const smc = reinterpret_cast<float2*>(smem_raw);
+    B2S_DYN_SMEM_F4(sm4);
     const int tid = (int)threadIdx.x;
     const int grp = tid / G;
     const int t = tid & (G - 1);
-    const int lane0 = tid & 16;                          // first lane of this duo inside the warp
-    float4* const buf = reinterpret_cast<float4*>(smem_raw + (size_t)DP::TAB * sizeof(float2)) + grp * DP::BUF;
+    float4* const buf = sm4 + DP::TAB + grp * DP::BUF;
 
     // ---- stage the constant tables (once per CTA); the PSD scale goes into the window ----
     {
         const float csc = sqrtf(0.5f * p.scale);
         const float2* w2 = reinterpret_cast<const float2*>(p.window);
-        for (int i = tid; i < M; i += DP::NT) {
-            const float2 w = __ldg(w2 + i);
-            smc[DP::OFF_WIN + i] = cmk(w.x * csc, w.y * csc);
+        for (int i = tid; i < 8 * 16; i += DP::NT) {
+            const int j = i >> 4, l = i & 15;
+            const float2 wa = __ldg(w2 + l + 16 * (2 * j)), wb = __ldg(w2 + l + 16 * (2 * j + 1));
+            sm4[DP::OFF_WIN + i] = make_float4(wa.x * csc, wa.y * csc, wb.x * csc, wb.y * csc);
+            // W_256^(t' q): t' = 0 is 1
+            const float2 ta = (j == 0) ? cmk(1.f, 0.f) : __ldg(p.tw + PL::OFF_P1 + (2 * j - 1) * 16 + l);
+            const float2 tb = __ldg(p.tw + PL::OFF_P1 + (2 * j) * 16 + l);
+            sm4[DP::OFF_TW1 + i] = make_float4(ta.x, ta.y, tb.x, tb.y);
+            if (j < 4) {
+                const float2 pa = __ldg(p.tw + PL::OFF_POST + l + 16 * (2 * j));
+                const float2 pb = __ldg(p.tw + PL::OFF_POST + l + 16 * (2 * j + 1));
+                sm4[DP::OFF_TWP + i] = make_float4(pa.x, pa.y, pb.x, pb.y);
+            }
         }
-        for (int i = tid; i < 15 * 16; i += DP::NT) smc[DP::OFF_TW1 + i] = __ldg(p.tw + PL::OFF_P1 + i);
-        for (int i = tid; i < 8 * 16; i += DP::NT) smc[DP::OFF_TWP + i] = __ldg(p.tw + PL::OFF_POST + i);
     }
     __syncthreads();
 
     const int kout = p.kmax - p.kmin + 1;
-    const int partner = lane0 | ((16 - t) & 15);
+    const int partner = (tid & 16) | ((16 - t) & 15);
     const bool is0 = (t == 0);
     const float edge = is0 ? 0.5f : 1.0f;                // DC / Nyquist carry scale, not 2 scale
 
@@ -152,57 +197,38 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kerne
         const Tin* const xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop;
         float* const ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
 
-        // raw samples of the duo: slot i <-> complex index t + 16 i relative to frame f
+        // raw samples of the duo: slot i <-> complex index t + 16 i relative to frame f.
+        // Slots 16.. belong to frame B only; when the run has no frame B they re-read the
+        // previous S slots instead (valid addresses, values unused).
         float2 cur[NCUR];
         {
             const Tin* const xf = xb + (long long)f_begin * p.hop + 2 * t;
-            const bool hasB = f_begin + 1 < f_end;
+            const Tin* const xfB = xf - ((f_begin + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
-            for (int i = 0; i < NCUR; ++i)
-                cur[i] = (i < 16 || hasB) ? Loader<Tin>::ld2(xf + 32 * i) : cmk(0.f, 0.f);
+            for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xf : xfB) + 32 * i);
         }
-
-        for (int f = f_begin;; f += 2) {
+        // the two duos of a warp run the same trip count (the longer run's); a duo past its
+        // last frame recomputes with its stores predicated off
+        int ntrip = uvalid ? (f_end - f_begin + 1) >> 1 : 0;
+        {
+            const int other = __shfl_xor_sync(0xffffffffu, ntrip, 16);
+            ntrip = ntrip > other ? ntrip : other;
+        }
+        int f = f_begin;
+        for (int it = 0; it < ntrip; ++it, f += 2) {
             const bool actA = uvalid && (f < f_end);
             const bool actB = uvalid && (f + 1 < f_end);
-            if (!__any_sync(0xffffffffu, actA)) break;
 
             // ---- detrend + window, packing frame A (slots 0..15) and B (slots S..S+15) ----
+            // x' = x - (coarse mean) is exact or nearly so whatever the DC level; the mean r of
+            // x' is then removed inside the window multiply with a single rounding.
+            // (Measured and lost on B200: removing r after pass 0 through the transformed taps,
+            //  and computing the next duo's pivots one iteration ahead -- both lengthen live
+            //  ranges at 160+ registers and add shared-memory reads; 4-7 % slower.)
             cpx2 v[16];
             if (p.detrend) {
-                // pivots: the coarse mean of each frame, from per-slot sums added in a fixed
-                // frame-relative order (blocks of S slots first: A and B share NB - 1 blocks)
-                constexpr int NB = 16 / S;
-                float blk[NB + 1];
-#pragma unroll
-                for (int bi = 0; bi <= NB; ++bi) {
-                    float ss[S];
-#pragma unroll
-                    for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
-#pragma unroll
-                    for (int w = S / 2; w >= 1; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
-                    blk[bi] = ss[0];
-                }
-                float cA = blk[0], cB = blk[1];
-                if constexpr (NB == 2) {
-                    cA += blk[1];
-                    cB += blk[2];
-                } else if constexpr (NB == 4) {
-                    cA = (blk[0] + blk[1]) + (blk[2] + blk[3]);
-                    cB = (blk[1] + blk[2]) + (blk[3] + blk[4]);
-                } else {
-                    cA = ((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7]));
-                    cB = ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8]));
-                }
-#pragma unroll
-                for (int o = G / 2; o >= 1; o >>= 1) {
-                    cA += __shfl_xor_sync(0xffffffffu, cA, o);
-                    cB += __shfl_xor_sync(0xffffffffu, cB, o);
-                }
-                cA *= 1.0f / (float)DP::N;
-                cB *= 1.0f / (float)DP::N;
+                float cA, cB;
+                duo_coarse_means<S>(cur, cA, cB);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     v[i].re = cmk(cur[i].x - cA, cur[i + S].x - cB);
@@ -219,39 +245,42 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kerne
 #pragma unroll
                 for (int o = G / 2; o >= 1; o >>= 1)
                     tot = pk_add(tot, cmk(__shfl_xor_sync(0xffffffffu, tot.x, o), __shfl_xor_sync(0xffffffffu, tot.y, o)));
-                const float2 nr = pk_muls(tot, -1.0f / (float)DP::N);     // - mean of the residual
+                const float2 nr = pk_muls(tot, -1.0f / (float)DP::N);      // - mean of x'
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 w = smc[DP::OFF_WIN + t + 16 * i];
-                    v[i].re = pk_fmas(v[i].re, w.x, pk_muls(nr, w.x));     // (x' - r) w, one rounding
-                    v[i].im = pk_fmas(v[i].im, w.y, pk_muls(nr, w.y));
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = sm4[DP::OFF_WIN + j * 16 + t];
+                    v[2 * j].re = pk_fmas(v[2 * j].re, w.x, pk_muls(nr, w.x));         // (x' - r) w, one rounding
+                    v[2 * j].im = pk_fmas(v[2 * j].im, w.y, pk_muls(nr, w.y));
+                    v[2 * j + 1].re = pk_fmas(v[2 * j + 1].re, w.z, pk_muls(nr, w.z));
+                    v[2 * j + 1].im = pk_fmas(v[2 * j + 1].im, w.w, pk_muls(nr, w.w));
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 w = smc[DP::OFF_WIN + t + 16 * i];
-                    v[i].re = cmk(cur[i].x * w.x, cur[i + S].x * w.x);
-                    v[i].im = cmk(cur[i].y * w.y, cur[i + S].y * w.y);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = sm4[DP::OFF_WIN + j * 16 + t];
+                    v[2 * j].re = cmk(cur[2 * j].x * w.x, cur[2 * j + S].x * w.x);
+                    v[2 * j].im = cmk(cur[2 * j].y * w.y, cur[2 * j + S].y * w.y);
+                    v[2 * j + 1].re = cmk(cur[2 * j + 1].x * w.z, cur[2 * j + 1 + S].x * w.z);
+                    v[2 * j + 1].im = cmk(cur[2 * j + 1].y * w.w, cur[2 * j + 1 + S].y * w.w);
                 }
             }
 
             // ---- next duo (frames f+2, f+3): keep the overlap, prefetch the 2 S new slots ----
+            // (unpredicated loads: past the end of the run the addresses are clamped to the
+            //  run's last frame, the values are never used)
             {
 #pragma unroll
                 for (int i = 0; i < KEEP; ++i) cur[i] = cur[i + 2 * S];
-                const bool nextA = actA && (f + 2 < f_end);
-                const bool nextB = actA && (f + 3 < f_end);
-                const Tin* const xn = xb + (long long)(f + 2) * p.hop + 2 * t;
+                const int fa = (f + 2 < f_end) ? f + 2 : f_end - 1;
+                const Tin* const xn = xb + (long long)fa * p.hop + 2 * t;
+                const Tin* const xnB = xn - ((fa + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
-                for (int i = KEEP; i < NCUR; ++i) {
-                    const bool need = (i < 16) ? nextA : nextB;
-                    cur[i] = need ? Loader<Tin>::ld2(xn + 32 * i) : cmk(0.f, 0.f);
-                }
+                for (int i = KEEP; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xn : xnB) + 32 * i);
             }
 
             // ---- pass 0: radix-16 over r (n = t + 16 r), then the 16 x 16 transpose ----
             c2radix16(v);
-            __syncwarp();                        // the previous duo's pass-1 reads are done
+            if constexpr (!ABL_NOXCHG) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const cpx2 z = v[perm16(q)];
@@ -265,12 +294,21 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kerne
                 const float4 q4 = buf[ROW * tt + t];
                 v[tt] = cpx2{cmk(q4.x, q4.y), cmk(q4.z, q4.w)};
             }
+            }
 #pragma unroll
-            for (int tt = 1; tt < 16; ++tt) v[tt] = c2mul(v[tt], smc[DP::OFF_TW1 + (tt - 1) * 16 + t]);
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = sm4[DP::OFF_TW1 + j * 16 + t];
+                if (j > 0) v[2 * j] = c2mul(v[2 * j], cmk(w.x, w.y));
+                v[2 * j + 1] = c2mul(v[2 * j + 1], cmk(w.z, w.w));
+            }
             c2radix16(v);
+            __syncwarp();                        // every lane has consumed its exchange reads
 
             // ---- real-FFT split + PSD: this lane owns bins k = t + 16 pp (pp < 8) and 256 - k ----
             float* const rowA = ob + (long long)f * kout;
+            float* const pA = rowA + t;                    // bin k = t + 16 pp of frame A
+            float* const pmA = rowA + (M - t);             // bin 256 - k
+            const int koutc = (MODE == EPI_PLAIN) ? (M + 1) : kout;
             float2 band = cmk(0.f, 0.f);
             auto put = [&](int k, float2 pw) {
                 if constexpr (MODE == EPI_GENERAL) {
@@ -283,22 +321,27 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kerne
                     if (k >= p.kmin && k <= p.kmax) band = pk_add(band, pw);
                 } else {
                     if (actA) rowA[k] = pw.x;
-                    if (actB) rowA[k + kout] = pw.y;
+                    if (actB) rowA[k + koutc] = pw.y;
                 }
             };
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) {
                 const cpx2 zk = v[perm16(pp)];
-                const cpx2 snd = v[perm16(15 - pp)];
+                // the mirror Z[256 - k] sits in the partner lane at p' = 15 - pp; lane 0 pairs
+                // k = 16 pp with 16 (16 - pp), which it holds itself (it is its own partner)
+                const cpx2 s15 = v[perm16(15 - pp)], s16 = v[perm16((16 - pp) & 15)];
+                const float s0 = is0 ? s16.re.x : s15.re.x, s1 = is0 ? s16.re.y : s15.re.y;
+                const float s2 = is0 ? s16.im.x : s15.im.x, s3 = is0 ? s16.im.y : s15.im.y;
                 cpx2 zm;
-                zm.re = cmk(__shfl_sync(0xffffffffu, snd.re.x, partner), __shfl_sync(0xffffffffu, snd.re.y, partner));
-                zm.im = cmk(__shfl_sync(0xffffffffu, snd.im.x, partner), __shfl_sync(0xffffffffu, snd.im.y, partner));
-                {   // lane 0 pairs k = 16 pp with 16 (16 - pp), which it holds itself
-                    const cpx2 own = v[perm16((16 - pp) & 15)];
-                    zm.re = is0 ? own.re : zm.re;
-                    zm.im = is0 ? own.im : zm.im;
+                if constexpr (ABL_NOSHFL) {
+                    zm.re = cmk(s0, s1);
+                    zm.im = cmk(s2, s3);
+                } else {
+                    zm.re = cmk(__shfl_sync(0xffffffffu, s0, partner), __shfl_sync(0xffffffffu, s1, partner));
+                    zm.im = cmk(__shfl_sync(0xffffffffu, s2, partner), __shfl_sync(0xffffffffu, s3, partner));
                 }
-                const float2 w = smc[DP::OFF_TWP + pp * 16 + t];
+                const float4 w4 = sm4[DP::OFF_TWP + (pp >> 1) * 16 + t];
+                const float2 w = (pp & 1) ? cmk(w4.z, w4.w) : cmk(w4.x, w4.y);
                 const cpx2 e{pk_add(zk.re, zm.re), pk_sub(zk.im, zm.im)};      // 2E = zk + conj(zm)
                 const cpx2 o{pk_add(zk.im, zm.im), pk_sub(zm.re, zk.re)};      // 2O = -i (zk - conj(zm))
                 const cpx2 tw = c2mul(o, w);
@@ -309,9 +352,23 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_kerne
                     pk = pk_muls(pk, edge);
                     pm = pk_muls(pm, edge);
                 }
-                const int k = t + 16 * pp;
-                put(k, pk);
-                put(M - k, pm);
+                if constexpr (ABL_NOSTG) {
+                    band = pk_add(band, pk_add(pk, pm));
+                    if (pp == 7 && band.x == 123.456f) pA[0] = band.y;
+                } else if constexpr (MODE == EPI_PLAIN) {
+                    if (actA) {
+                        pA[16 * pp] = pk.x;
+                        pmA[-16 * pp] = pm.x;
+                    }
+                    if (actB) {
+                        pA[koutc + 16 * pp] = pk.y;
+                        pmA[koutc - 16 * pp] = pm.y;
+                    }
+                } else {
+                    const int k = t + 16 * pp;
+                    put(k, pk);
+                    put(M - k, pm);
+                }
             }
             {   // k = 128: X = conj(Z[128]), held by lane 0
                 const cpx2 z = v[perm16(8)];

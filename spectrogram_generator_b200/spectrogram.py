@@ -319,12 +319,12 @@ class _Streams:
 
 
 def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=True, want_sum=False,
-                   kmin=0, kmax=None, out_mode=0, db_floor=0.0):
+                   sum_scale=1.0, kmin=0, kmax=None, out_mode=0, db_floor=0.0):
     """Host arrays in, host arrays out: H2D copy, kernels and D2H copy of successive
     chunks overlap on three streams (PCIe is full duplex), so the end-to-end time tends
     to max(H2D, D2H) instead of their sum.  Chunks are runs of sweeps for batches and
     frame ranges (with their nperseg-hop halo of samples) for a single long recording.
-    Returns (S_host [B, F, Kout] or None, sum_dev [F, Kout] or None)."""
+    Returns (S_host [B, F, Kout] or None, sum_scale * sum_dev [F, Kout] or None)."""
     eng = engine()
     B, n = x2d.shape
     kmax = plan.nbins - 1 if kmax is None else kmax
@@ -372,7 +372,7 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_k)
                     h_out[b0:b1, f0:f1].copy_(S_d[b0:b1, f0:f1], non_blocking=True)
-        total = eng.batch_sum(S_d, 1.0) if want_sum else None
+        total = eng.batch_sum(S_d, sum_scale) if want_sum else None
         if per_sweep:
             s_out.synchronize()
         cur.synchronize()             # x_d / S_d were used on side streams: keep them alive until here
@@ -451,9 +451,10 @@ def mean_spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=No
     eng = engine()
     eng.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    S, total = _host_pipeline(x, plan, dev, out_dtype, per_sweep=return_per_sweep, want_sum=True)
+    S, total = _host_pipeline(x, plan, dev, out_dtype, per_sweep=return_per_sweep, want_sum=True,
+                              sum_scale=1.0 / x.shape[0])
     with torch.cuda.device(dev):
-        mean = np.moveaxis(_to_host(total * (1.0 / x.shape[0]), out_dtype), -1, -2)
+        mean = np.moveaxis(_to_host(total, out_dtype), -1, -2)
     if return_per_sweep:
         return f, t, mean, np.moveaxis(S, -1, -2)
     return f, t, mean

@@ -1,0 +1,110 @@
+// Stand-alone timing harness for the frame-duo kernel variants (tuning tool, not product):
+// C2 shape (1000 x 40000, nperseg 512, hop 128), CUDA events, prints ms per variant and a
+// checksum so variants can be compared.   Build: see tools/ubench/build.sh
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "b2s_dispatch.hpp"
+
+using namespace b2s;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+struct Ctx {
+    StftArgs a;
+    float2* tw;
+    int sms;
+};
+
+template <typename K>
+void run(const char* name, K kern, int nt, size_t smem, int fpc, Ctx& c, int iters = 20) {
+    if (const char* ex = getenv("EXTRA_SMEM")) smem += (size_t)atoi(ex);      // lowers the occupancy
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
+    StftParams p{};
+    std::string err;
+    const long long resident = (long long)c.sms * occ;
+    if (plan_stft(c.a, fpc, resident * fpc, p, err) < 0) { printf("plan: %s\n", err.c_str()); exit(1); }
+    if (const char* cf = getenv("CHUNK")) {
+        p.chunk_frames = atoi(cf);
+        p.units_per_signal = (c.a.nframes + p.chunk_frames - 1) / p.chunk_frames;
+        p.n_units = p.units_per_signal * c.a.batch;
+    }
+    p.tw = c.tw;
+    const long long need = (p.n_units + fpc - 1) / fpc;
+    const unsigned grid = (unsigned)(need < resident ? need : resident);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaMemset(c.a.out, 0, sizeof(float) * c.a.batch * c.a.out_batch_stride));
+    for (int i = 0; i < 3; ++i) kern<<<grid, nt, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    float best = 1e9f, tot = 0.f;
+    for (int i = 0; i < iters; ++i) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, nt, smem>>>(p);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best;
+        tot += ms;
+    }
+    CK(cudaGetLastError());
+    // checksum over a sample of the output
+    std::vector<float> h(1 << 20);
+    CK(cudaMemcpy(h.data(), c.a.out, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    double cs = 0;
+    for (float v : h) cs += v;
+    const double bytes = 4.0 * c.a.batch * c.a.n + 4.0 * c.a.batch * c.a.nframes * (c.a.nperseg / 2 + 1);
+    printf("%-34s occ %d grid %4u chunk %2d  mean %.4f ms  min %.4f ms  %.1f GB/s  frac %.3f  checksum %.9g\n", name, occ, grid,
+           p.chunk_frames, tot / iters, best, bytes / (best * 1e-3) / 1e9, bytes / (best * 1e-3) / 1e9 / 6537.0, cs);
+}
+
+int main(int argc, char** argv) {
+    const int B = 1000, N = 40000, NP = 512, HOP = (argc > 1) ? atoi(argv[1]) : 128;
+    const int F = (N - NP) / HOP + 1, K = NP / 2 + 1;
+    Ctx c;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    c.sms = prop.multiProcessorCount;
+    std::vector<float> hx((size_t)B * N), hw(NP), htw;
+    unsigned s = 12345u;
+    for (auto& v : hx) { s = s * 1664525u + 1013904223u; v = ((s >> 8) * (1.0f / 16777216.0f) - 0.5f) * 2.f + 0.25f; }
+    for (int i = 0; i < NP; ++i) hw[i] = 0.5f - 0.5f * cosf(2.f * 3.14159265358979f * i / NP);
+    make_tables(NP, htw);
+    float *dx, *dw, *dout;
+    CK(cudaMalloc(&dx, hx.size() * 4));
+    CK(cudaMalloc(&dw, NP * 4));
+    CK(cudaMalloc(&dout, (size_t)B * F * K * 4));
+    CK(cudaMalloc(&c.tw, htw.size() * 4));
+    CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, hw.data(), NP * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.tw, htw.data(), htw.size() * 4, cudaMemcpyHostToDevice));
+    c.a = StftArgs{dx, 0, B, N, N, NP, HOP, dw, 1, 1.0 / (20000.0 * 192.0), 0, 0.f, 0, NP / 2, 0, F, dout, (long long)F * K, 0};
+    using WP = WarpPlan<9>;
+    using DP = DuoPlan;
+    if (HOP == 128) {
+        run("warp<9,float,4,0>", stft_psd_warp_kernel<9, float, 4, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo<float,4,0>", stft_psd_duo_kernel<float, 4, 0, 3, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+        run("duo OPT=8  no STG", stft_psd_duo_kernel<float, 4, 0, 3, 8>, DP::NT, DP::SMEM, DP::FPC, c);
+        run("duo OPT=16 no exchange", stft_psd_duo_kernel<float, 4, 0, 3, 16>, DP::NT, DP::SMEM, DP::FPC, c);
+        run("duo OPT=32 no mirror shfl", stft_psd_duo_kernel<float, 4, 0, 3, 32>, DP::NT, DP::SMEM, DP::FPC, c);
+        run("duo OPT=56 none of the three", stft_psd_duo_kernel<float, 4, 0, 3, 56>, DP::NT, DP::SMEM, DP::FPC, c);
+        c.a.detrend = 0;
+        run("duo OPT=0 detrend off", stft_psd_duo_kernel<float, 4, 0, 3, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+        run("duo OPT=56 detrend off", stft_psd_duo_kernel<float, 4, 0, 3, 56>, DP::NT, DP::SMEM, DP::FPC, c);
+        c.a.detrend = 1;
+    } else if (HOP == 64) {
+        run("warp<9,float,2,0>", stft_psd_warp_kernel<9, float, 2, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo<float,2,0,MINB=3>", stft_psd_duo_kernel<float, 2, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 256) {
+        run("warp<9,float,8,0>", stft_psd_warp_kernel<9, float, 8, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo<float,8,0,MINB=3>", stft_psd_duo_kernel<float, 8, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    }
+    return 0;
+}
