@@ -159,6 +159,13 @@ int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
 struct CudaLauncher {
     cudaStream_t stream;
     bool allow_duo = true;
+    bool duo1024 = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int duo_cta(const b2s::StftArgs& a) {
+        using DP = b2s::DuoCtaPlan<LOG2N>;
+        return launch_any((const void*)b2s::stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
+                          stream);
+    }
     template <typename Tin, int S, int MODE>
     int duo(const b2s::StftArgs& a) {
         using DP = b2s::DuoPlan;
@@ -207,6 +214,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
     CudaLauncher L{(cudaStream_t)stream};
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     return b2s::dispatch_stft(a, L);
 }
 

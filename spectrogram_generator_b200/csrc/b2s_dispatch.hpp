@@ -9,13 +9,17 @@
 //   template <int LOG2N, typename Tin, int SHIFT, int MODE> int warp(const StftArgs&);
 //   template <int LOG2N, typename Tin, int MODE>            int cta(const StftArgs&);
 //   template <typename Tin, int S, int MODE>                int duo(const StftArgs&);
-//   bool allow_duo;
+//   template <int LOG2N, typename Tin, int MODE>            int duo_cta(const StftArgs&);
+//   bool allow_duo, duo1024;
 //
 //   nperseg == 512 with hop in {64, 128, 256} (2-element aligned frames) takes the packed
-//   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh).
+//   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh);
+//   nperseg 1024 / 2048 / 4096 (any hop) take stft_psd_duo_cta_kernel (b2s_duo_cta_kernel.cuh):
+//   measured 7-22 % faster than the one-frame kernels on B200 (tools/ubench/duo_bench).
 #pragma once
 
 #include "b2s_host.hpp"
+#include "b2s_duo_cta_kernel.cuh"
 #include "b2s_duo_kernel.cuh"
 #include "b2s_warp_kernel.cuh"
 
@@ -79,9 +83,11 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
         case 7: return dispatch_warp_shift<7, Tin, MODE>(a, L, shift);
         case 8: return dispatch_warp_shift<8, Tin, MODE>(a, L, shift);
         case 9: return dispatch_warp_shift<9, Tin, MODE>(a, L, shift);
-        case 10: return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
-        case 11: return L.template cta<11, Tin, MODE>(a);
-        case 12: return L.template cta<12, Tin, MODE>(a);
+        case 10:
+            if (L.allow_duo && L.duo1024) return L.template duo_cta<10, Tin, MODE>(a);
+            return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
+        case 11: return L.allow_duo ? L.template duo_cta<11, Tin, MODE>(a) : L.template cta<11, Tin, MODE>(a);
+        case 12: return L.allow_duo ? L.template duo_cta<12, Tin, MODE>(a) : L.template cta<12, Tin, MODE>(a);
         case 13: return L.template cta<13, Tin, MODE>(a);
         case 14: return L.template cta<14, Tin, MODE>(a);
         default: return B2S_ERR_UNSUPPORTED;

@@ -353,22 +353,24 @@ B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stri
                                  int rows_per_slab, long long elems, float* __restrict__ out,
                                  float post_scale) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int slab = (int)blockIdx.y;
+    // the last slabs are the rows the STFT kernel wrote last: take them first, while they are
+    // still in L2
+    const int slab = (int)(gridDim.y - 1 - blockIdx.y);
     if (e >= elems) return;
     const int r0 = slab * rows_per_slab;
     const int r1 = (r0 + rows_per_slab < batch) ? r0 + rows_per_slab : batch;
     const float* q = in + (long long)r0 * in_stride + e;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
     int r = r0;
-    for (; r + 4 <= r1; r += 4) {
-        a0 += q[0];
-        a1 += q[in_stride];
-        a2 += q[2 * in_stride];
-        a3 += q[3 * in_stride];
-        q += 4 * in_stride;
+    for (; r + 8 <= r1; r += 8) {         // 8 independent loads in flight per thread
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += q[j * in_stride];
+        q += 8 * in_stride;
     }
-    for (; r < r1; ++r) { a0 += q[0]; q += in_stride; }
-    out[(long long)slab * elems + e] = ((a0 + a1) + (a2 + a3)) * post_scale;
+    for (; r < r1; ++r) { a[0] += q[0]; q += in_stride; }
+    out[(long long)slab * elems + e] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * post_scale;
 }
 
 

@@ -18,6 +18,13 @@ struct EmuLauncher {
     StftParams p;
     unsigned grid;
     bool allow_duo = true;
+    bool duo1024 = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int duo_cta(const StftArgs&) {
+        using DP = DuoCtaPlan<LOG2N>;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>(p); });
+        return 0;
+    }
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs&) {
         using DP = DuoPlan;
@@ -73,6 +80,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     L.p.tw = reinterpret_cast<const float2*>(tw.data());
     if (L.p.n_units == 0) return 0;
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     return dispatch_stft(a, L);
 }
 

@@ -218,3 +218,28 @@ def test_frame_duo_kernel(emu, hop, nframes_extra, detrend):
     np.testing.assert_allclose(band, a[:, :, 3:41].astype(np.float64).sum(axis=-1), rtol=2e-6)
     edge = emu.band_power(x, plan, 0, 256, chunk=2)
     np.testing.assert_allclose(edge, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
+
+
+@pytest.mark.parametrize("nperseg,hop", [(2048, 512), (2048, 333), (4096, 1024), (4096, 3584)])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):
+    """nperseg 2048 / 4096 run on the packed two-frames-per-group CTA kernel (any hop, the odd
+    one takes the scalar-load path): odd frame counts, runs cut at odd lengths, crop / frame
+    range / band power, float64 samples; a frame's result must not depend on the chunking."""
+    nfr = 5
+    n = nperseg + hop * (nfr - 1) + 3
+    x = signal(2, n, nperseg + hop + 1, dc=-3.0 if detrend else 0.0)
+    kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = plan_for(n, 48000.0, **kw)
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    a = emu.stft_psd(x, plan, chunk=3, grid=1)
+    b = emu.stft_psd(x, plan, chunk=2, grid=2)
+    assert_parity(a, So, what=f"duo cta {nperseg}/{hop}")
+    assert np.array_equal(a, b)
+    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
+    part = emu.stft_psd(x, plan, kmin=3, kmax=900, frame0=1, nframes=nfr - 2, chunk=4)
+    assert np.array_equal(part, a[:, 1:nfr - 1, 3:901])
+    band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
+    np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
