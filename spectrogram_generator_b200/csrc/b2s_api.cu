@@ -160,6 +160,13 @@ struct CudaLauncher {
     cudaStream_t stream;
     bool allow_duo = true;
     bool duo1024 = true;
+    bool allow_duo4 = true;
+    template <int LOG2N, typename Tin, int S, int MODE>
+    int duo4(const b2s::StftArgs& a) {
+        using DP = b2s::Duo4Plan<LOG2N>;
+        return launch_any((const void*)b2s::stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
+                          stream);
+    }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const b2s::StftArgs& a) {
         using DP = b2s::DuoCtaPlan<LOG2N>;
@@ -215,6 +222,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     CudaLauncher L{(cudaStream_t)stream};
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
+    if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
     return b2s::dispatch_stft(a, L);
 }
 

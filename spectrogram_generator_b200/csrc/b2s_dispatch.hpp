@@ -10,15 +10,19 @@
 //   template <int LOG2N, typename Tin, int MODE>            int cta(const StftArgs&);
 //   template <typename Tin, int S, int MODE>                int duo(const StftArgs&);
 //   template <int LOG2N, typename Tin, int MODE>            int duo_cta(const StftArgs&);
-//   bool allow_duo, duo1024;
+//   template <int LOG2N, typename Tin, int S, int MODE>     int duo4(const StftArgs&);
+//   bool allow_duo, duo1024, allow_duo4;
 //
 //   nperseg == 512 with hop in {64, 128, 256} (2-element aligned frames) takes the packed
 //   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh);
-//   nperseg 1024 / 2048 / 4096 (any hop) take stft_psd_duo_cta_kernel (b2s_duo_cta_kernel.cuh):
-//   measured 7-22 % faster than the one-frame kernels on B200 (tools/ubench/duo_bench).
+//   nperseg 1024 / 2048 / 4096 with hop = S * nperseg/16, S in {2, 4, 8} (2-element aligned
+//   frames) take the four-step stft_psd_duo4_kernel (b2s_duo4_kernel.cuh); with any other hop
+//   stft_psd_duo_cta_kernel (b2s_duo_cta_kernel.cuh), measured 7-22 % faster than the one-frame
+//   kernels on B200 (tools/ubench/duo_bench).
 #pragma once
 
 #include "b2s_host.hpp"
+#include "b2s_duo4_kernel.cuh"
 #include "b2s_duo_cta_kernel.cuh"
 #include "b2s_duo_kernel.cuh"
 #include "b2s_warp_kernel.cuh"
@@ -73,6 +77,28 @@ int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
     return L.template warp<LOG2N, Tin, 0, MODE>(a);
 }
 
+// four-step duo kernel: nperseg 1024..4096, hop = S * nperseg/16, S in {2, 4, 8}
+inline int duo4_slots(const StftArgs& a) {
+    if (!frames_vec_aligned(a)) return 0;
+    const long long n16 = a.nperseg / 16;
+    if (a.hop % n16) return 0;
+    const long long s = a.hop / n16;
+    return (s == 2 || s == 4 || s == 8) ? (int)s : 0;
+}
+
+template <int LOG2N, typename Tin, int MODE, class Launcher>
+int dispatch_duo_big(const StftArgs& a, Launcher& L) {
+    if (L.allow_duo4) {
+        switch (duo4_slots(a)) {
+            case 2: return L.template duo4<LOG2N, Tin, 2, MODE>(a);
+            case 4: return L.template duo4<LOG2N, Tin, 4, MODE>(a);
+            case 8: return L.template duo4<LOG2N, Tin, 8, MODE>(a);
+            default: break;
+        }
+    }
+    return L.template duo_cta<LOG2N, Tin, MODE>(a);
+}
+
 template <typename Tin, int MODE, class Launcher>
 int dispatch_tg(const StftArgs& a, Launcher& L) {
     const int log2n = ilog2_exact(a.nperseg);
@@ -84,10 +110,10 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
         case 8: return dispatch_warp_shift<8, Tin, MODE>(a, L, shift);
         case 9: return dispatch_warp_shift<9, Tin, MODE>(a, L, shift);
         case 10:
-            if (L.allow_duo && L.duo1024) return L.template duo_cta<10, Tin, MODE>(a);
+            if (L.allow_duo && L.duo1024) return dispatch_duo_big<10, Tin, MODE>(a, L);
             return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
-        case 11: return L.allow_duo ? L.template duo_cta<11, Tin, MODE>(a) : L.template cta<11, Tin, MODE>(a);
-        case 12: return L.allow_duo ? L.template duo_cta<12, Tin, MODE>(a) : L.template cta<12, Tin, MODE>(a);
+        case 11: return L.allow_duo ? dispatch_duo_big<11, Tin, MODE>(a, L) : L.template cta<11, Tin, MODE>(a);
+        case 12: return L.allow_duo ? dispatch_duo_big<12, Tin, MODE>(a, L) : L.template cta<12, Tin, MODE>(a);
         case 13: return L.template cta<13, Tin, MODE>(a);
         case 14: return L.template cta<14, Tin, MODE>(a);
         default: return B2S_ERR_UNSUPPORTED;

@@ -19,6 +19,13 @@ struct EmuLauncher {
     unsigned grid;
     bool allow_duo = true;
     bool duo1024 = true;
+    bool allow_duo4 = true;
+    template <int LOG2N, typename Tin, int S, int MODE>
+    int duo4(const StftArgs&) {
+        using DP = Duo4Plan<LOG2N>;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>(p); });
+        return 0;
+    }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs&) {
         using DP = DuoCtaPlan<LOG2N>;
@@ -81,6 +88,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (L.p.n_units == 0) return 0;
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
+    if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
 

@@ -243,3 +243,29 @@ def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:901])
     band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
+
+
+@pytest.mark.parametrize("nperseg,hop", [(1024, 256), (1024, 128), (1024, 512), (2048, 512), (2048, 1024),
+                                         (4096, 1024), (4096, 512)])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_four_step_duo_kernel(emu, nperseg, hop, detrend):
+    """nperseg 1024 / 2048 / 4096 with hop = S * nperseg/16 run on the four-step duo kernel
+    (256-point sub-transforms per half-warp + fused radix-R final stage): odd frame counts, runs
+    cut at odd lengths, crop / frame range / band power, float64 samples; chunking-invariant."""
+    nfr = 5
+    n = nperseg + hop * (nfr - 1) + 3
+    x = signal(2, n, nperseg + hop + 1, dc=-3.0 if detrend else 0.0)
+    kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = plan_for(n, 48000.0, **kw)
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    a = emu.stft_psd(x, plan, chunk=3, grid=1)
+    b = emu.stft_psd(x, plan, chunk=2, grid=2)
+    assert_parity(a, So, what=f"duo4 {nperseg}/{hop}")
+    assert np.array_equal(a, b)
+    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
+    part = emu.stft_psd(x, plan, kmin=3, kmax=500, frame0=1, nframes=nfr - 2, chunk=4)
+    assert np.array_equal(part, a[:, 1:nfr - 1, 3:501])
+    band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
+    np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)

@@ -98,6 +98,10 @@ int main_cta(int B, int N, int HOP) {
         run("cta<LOG2N,float,2,0>", stft_psd_kernel<LOG2N, float, 2, 0>, PL::NT, PL::SMEM, PL::FPC, c);
     }
     run("duo_cta<LOG2N,float,0>", stft_psd_duo_cta_kernel<LOG2N, float, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    using D4 = Duo4Plan<LOG2N>;
+    if (HOP * 16 == NP * 4) run("duo4<LOG2N,float,4,0>", stft_psd_duo4_kernel<LOG2N, float, 4, 0>, D4::NT, D4::SMEM, D4::FPC, c);
+    if (HOP * 16 == NP * 2) run("duo4<LOG2N,float,2,0>", stft_psd_duo4_kernel<LOG2N, float, 2, 0>, D4::NT, D4::SMEM, D4::FPC, c);
+    if (HOP * 16 == NP * 8) run("duo4<LOG2N,float,8,0>", stft_psd_duo4_kernel<LOG2N, float, 8, 0>, D4::NT, D4::SMEM, D4::FPC, c);
     return 0;
 }
 
