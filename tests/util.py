@@ -71,7 +71,8 @@ class Emulator:
 
     def __init__(self):
         import __graft_entry__ as ge
-        self.lib = ctypes.CDLL(ge.build_emulator())
+        # B2S_EMU_LIB: an alternative build of the harness (e.g. -fsanitize=address, see tests/emu/README)
+        self.lib = ctypes.CDLL(os.environ.get("B2S_EMU_LIB") or ge.build_emulator())
         c = ctypes
         self.lib.emu_stft_psd.restype = c.c_int
         self.lib.emu_stft_psd.argtypes = [c.c_void_p, c.c_int, c.c_longlong, c.c_longlong, c.c_longlong,
