@@ -161,6 +161,11 @@ struct CudaLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    template <typename Tin, int S, int MODE>
+    int duo256(const b2s::StftArgs& a) {
+        using DP = b2s::Duo256Plan;
+        return launch_any((const void*)b2s::stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
+    }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const b2s::StftArgs& a) {
         using DP = b2s::Duo4Plan<LOG2N>;

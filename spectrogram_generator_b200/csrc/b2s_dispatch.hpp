@@ -11,10 +11,12 @@
 //   template <typename Tin, int S, int MODE>                int duo(const StftArgs&);
 //   template <int LOG2N, typename Tin, int MODE>            int duo_cta(const StftArgs&);
 //   template <int LOG2N, typename Tin, int S, int MODE>     int duo4(const StftArgs&);
+//   template <typename Tin, int S, int MODE>                int duo256(const StftArgs&);
 //   bool allow_duo, duo1024, allow_duo4;
 //
 //   nperseg == 512 with hop in {64, 128, 256} (2-element aligned frames) takes the packed
-//   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh);
+//   two-frames-per-lane stft_psd_duo_kernel<Tin, S, MODE> instead (b2s_duo_kernel.cuh), and
+//   nperseg == 256 with hop in {32, 64, 128} stft_psd_duo256_kernel (b2s_duo256_kernel.cuh);
 //   nperseg 1024 / 2048 / 4096 with hop = S * nperseg/16, S in {2, 4, 8} (2-element aligned
 //   frames) take the four-step stft_psd_duo4_kernel (b2s_duo4_kernel.cuh); with any other hop
 //   stft_psd_duo_cta_kernel (b2s_duo_cta_kernel.cuh), measured 7-22 % faster than the one-frame
@@ -22,6 +24,7 @@
 #pragma once
 
 #include "b2s_host.hpp"
+#include "b2s_duo256_kernel.cuh"
 #include "b2s_duo4_kernel.cuh"
 #include "b2s_duo_cta_kernel.cuh"
 #include "b2s_duo_kernel.cuh"
@@ -64,6 +67,16 @@ int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
     if constexpr (LOG2N == 9) {
         const int s = L.allow_duo ? duo_slots(a, LOG2N) : 0;
         if (s) return dispatch_duo<Tin, MODE>(a, L, s);
+    }
+    if constexpr (LOG2N == 8) {
+        if (L.allow_duo && frames_vec_aligned(a)) {
+            switch (a.hop) {
+                case 32: return L.template duo256<Tin, 2, MODE>(a);
+                case 64: return L.template duo256<Tin, 4, MODE>(a);
+                case 128: return L.template duo256<Tin, 8, MODE>(a);
+                default: break;
+            }
+        }
     }
     if constexpr (LOG2N >= 8 && sizeof(Tin) == 4) {
         switch (shift) {

@@ -20,6 +20,12 @@ struct EmuLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    template <typename Tin, int S, int MODE>
+    int duo256(const StftArgs&) {
+        using DP = Duo256Plan;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo256_kernel<Tin, S, MODE>(p); });
+        return 0;
+    }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const StftArgs&) {
         using DP = Duo4Plan<LOG2N>;

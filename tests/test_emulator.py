@@ -191,14 +191,13 @@ def test_fused_band_power(emu, nperseg):
     np.testing.assert_allclose(band, So[:, kmin:kmax + 1, :].sum(axis=1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("hop", [64, 128, 256])
+@pytest.mark.parametrize("nperseg,hop", [(512, 64), (512, 128), (512, 256), (256, 32), (256, 64), (256, 128)])
 @pytest.mark.parametrize("nframes_extra", [0, 1])
 @pytest.mark.parametrize("detrend", ["constant", False])
-def test_frame_duo_kernel(emu, hop, nframes_extra, detrend):
-    """nperseg 512 with hop 64/128/256 runs on the packed two-frames-per-lane kernel: odd and
-    even frame counts, runs cut at odd lengths, crop / frame range / band power, float64
-    samples, against the oracle; the result of a frame must not depend on the chunking."""
-    nperseg = 512
+def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):
+    """nperseg 512 (hop 64/128/256) and 256 (hop 32/64/128) run on the packed two-frames-per-lane
+    kernels: odd and even frame counts, runs cut at odd lengths, crop / frame range / band power,
+    float64 samples, against the oracle; the result of a frame must not depend on the chunking."""
     nfr = 6 + nframes_extra
     n = nperseg + hop * (nfr - 1) + 5
     x = signal(3, n, nperseg + hop + nframes_extra, dc=-3.0 if detrend else 0.0)
@@ -209,14 +208,14 @@ def test_frame_duo_kernel(emu, hop, nframes_extra, detrend):
     So = np.moveaxis(So, -1, -2)
     a = emu.stft_psd(x, plan, chunk=3, grid=1)           # odd run length: last duo of a run is half empty
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
-    assert_parity(a, So, what=f"duo 512/{hop}")
+    assert_parity(a, So, what=f"duo {nperseg}/{hop}")
     assert np.array_equal(a, b)
     assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
     part = emu.stft_psd(x, plan, kmin=3, kmax=40, frame0=1, nframes=nfr - 2, chunk=4)
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:41])
     band = emu.band_power(x, plan, 3, 40, chunk=3)
     np.testing.assert_allclose(band, a[:, :, 3:41].astype(np.float64).sum(axis=-1), rtol=2e-6)
-    edge = emu.band_power(x, plan, 0, 256, chunk=2)
+    edge = emu.band_power(x, plan, 0, nperseg // 2, chunk=2)
     np.testing.assert_allclose(edge, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
 
 

@@ -105,7 +105,45 @@ int main_cta(int B, int N, int HOP) {
     return 0;
 }
 
+int main_256(int B, int N, int HOP) {
+    const int NP = 256;
+    const int F = (N - NP) / HOP + 1, K = NP / 2 + 1;
+    Ctx c;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    c.sms = prop.multiProcessorCount;
+    std::vector<float> hx((size_t)B * N), hw(NP), htw;
+    unsigned s = 12345u;
+    for (auto& v : hx) { s = s * 1664525u + 1013904223u; v = ((s >> 8) * (1.0f / 16777216.0f) - 0.5f) * 2.f + 0.25f; }
+    for (int i = 0; i < NP; ++i) hw[i] = 0.5f - 0.5f * cosf(2.f * 3.14159265358979f * i / NP);
+    make_tables(NP, htw);
+    float *dx, *dw, *dout;
+    CK(cudaMalloc(&dx, hx.size() * 4));
+    CK(cudaMalloc(&dw, NP * 4));
+    CK(cudaMalloc(&dout, (size_t)B * F * K * 4));
+    CK(cudaMalloc(&c.tw, htw.size() * 4));
+    CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, hw.data(), NP * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.tw, htw.data(), htw.size() * 4, cudaMemcpyHostToDevice));
+    c.a = StftArgs{dx, 0, B, N, N, NP, HOP, dw, 1, 1.0 / (20000.0 * 96.0), 0, 0.f, 0, NP / 2, 0, F, dout, (long long)F * K, 0};
+    printf("nperseg %d hop %d batch %d n %d\n", NP, HOP, B, N);
+    using WP = WarpPlan<8>;
+    using DP = Duo256Plan;
+    if (HOP == 64) {
+        run("warp<8,float,4,0>", stft_psd_warp_kernel<8, float, 4, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo256<float,4,0>", stft_psd_duo256_kernel<float, 4, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 32) {
+        run("warp<8,float,2,0>", stft_psd_warp_kernel<8, float, 2, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo256<float,2,0>", stft_psd_duo256_kernel<float, 2, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else {
+        run("warp<8,float,8,0>", stft_psd_warp_kernel<8, float, 8, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo256<float,8,0>", stft_psd_duo256_kernel<float, 8, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 4 && atoi(argv[1]) == 256) return main_256(atoi(argv[3]), atoi(argv[4]), atoi(argv[2]));
     if (argc > 4) {
         const int np = atoi(argv[1]), hop = atoi(argv[2]), b = atoi(argv[3]), n = atoi(argv[4]);
         if (np == 1024) return main_cta<10>(b, n, hop);
