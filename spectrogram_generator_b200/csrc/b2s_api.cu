@@ -278,7 +278,7 @@ int b2s_stft_band_power_f64(const double* x, long long batch, long long n, long 
                               0.f, kmin, kmax, frame0, nframes, out, out_batch_stride, stream, 1);
 }
 
-static const int kSumSlabRows = 64;
+static const int kSumSlabRows = 128;    // measured best on B200 with 16 loads in flight (tools/ubench/bsum)
 
 long long b2s_batch_sum_scratch_elems(long long batch, long long elems) {
     if (batch <= kSumSlabRows) return 0;

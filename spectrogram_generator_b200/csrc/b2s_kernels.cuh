@@ -360,17 +360,21 @@ B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stri
     const int r0 = slab * rows_per_slab;
     const int r1 = (r0 + rows_per_slab < batch) ? r0 + rows_per_slab : batch;
     const float* q = in + (long long)r0 * in_stride + e;
-    float a[8];
+    float a[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int j = 0; j < 16; ++j) a[j] = 0.f;
     int r = r0;
-    for (; r + 8 <= r1; r += 8) {         // 8 independent loads in flight per thread
+    for (; r + 16 <= r1; r += 16) {       // 16 independent loads in flight per thread
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += q[j * in_stride];
-        q += 8 * in_stride;
+        for (int j = 0; j < 16; ++j) a[j] += q[j * in_stride];
+        q += 16 * in_stride;
     }
     for (; r < r1; ++r) { a[0] += q[0]; q += in_stride; }
-    out[(long long)slab * elems + e] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * post_scale;
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+        for (int j = 0; j < w; ++j) a[j] += a[j + w];
+    out[(long long)slab * elems + e] = a[0] * post_scale;
 }
 
 

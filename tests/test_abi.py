@@ -33,8 +33,8 @@ def test_host_only_entries():
     assert lib.b2s_frame_count(40000, 512, 128) == 309
     assert lib.b2s_frame_count(441000, 1024, 256) == 1719
     assert lib.b2s_frame_count(100, 512, 128) == 0
-    assert lib.b2s_batch_sum_scratch_elems(1000, 79413) == 16 * 79413
-    assert lib.b2s_batch_sum_scratch_elems(64, 10) == 0
+    assert lib.b2s_batch_sum_scratch_elems(1000, 79413) == 8 * 79413      # slabs of 128 sweeps
+    assert lib.b2s_batch_sum_scratch_elems(128, 10) == 0
 
 
 def test_bad_arguments_are_reported_before_any_device_work():
