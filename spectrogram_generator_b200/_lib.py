@@ -22,8 +22,9 @@ B2S_OK, B2S_ERR_BAD_ARG, B2S_ERR_UNSUPPORTED, B2S_ERR_CUDA = 0, -1, -2, -3
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+BUILD_DIR = os.path.join(_HERE, "build")
 
 
 class B2SError(RuntimeError):
@@ -43,19 +44,35 @@ def _stale():
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libb200stft.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a (cross-compiles without a GPU) and link libb200stft.so.
+    The kernel instantiations are spread over several translation units (b2s_inst_*.cu), which
+    are compiled in parallel."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise B2SError("nvcc not found: cannot build libb200stft.so")
-    extra = ["-DB2S_EXPERIMENTS"] if os.environ.get("B2S_EXPERIMENTS") else []
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise B2SError("nvcc failed:\n" + res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src):
+        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+        res = subprocess.run([nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise B2SError(f"nvcc failed on {os.path.basename(src)}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, srcs))
     if verbose:
-        print(res.stderr)
+        for _, err in results:
+            print(err)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [o for o, _ in results] + ["-lcudart"],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise B2SError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

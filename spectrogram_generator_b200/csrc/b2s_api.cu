@@ -11,7 +11,8 @@
 #include <vector>
 
 #include "../../include/b2s.h"
-#include "b2s_dispatch.hpp"
+#include "b2s_aux_kernels.cuh"
+#include "b2s_launcher.hpp"
 
 namespace {
 
@@ -84,8 +85,8 @@ std::map<const void*, KernelState> g_kern;     // guarded by g_mu
 
 // One launch of an STFT kernel (either family): persistent grid sized from the
 // occupancy, work units sized from the grid (b2s::plan_stft).
-int launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
-               bool direct_table = false) {
+int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
+                    bool direct_table = false) {
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
@@ -156,60 +157,6 @@ int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
     return B2S_OK;
 }
 
-struct CudaLauncher {
-    cudaStream_t stream;
-    bool allow_duo = true;
-    bool duo1024 = true;
-    bool allow_duo4 = true;
-    template <typename Tin, int S, int MODE>
-    int duo256(const b2s::StftArgs& a) {
-        using DP = b2s::Duo256Plan;
-        return launch_any((const void*)b2s::stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
-    }
-    template <int LOG2N, typename Tin, int S, int MODE>
-    int duo4(const b2s::StftArgs& a) {
-        using DP = b2s::Duo4Plan<LOG2N>;
-        return launch_any((const void*)b2s::stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
-                          stream);
-    }
-    template <int LOG2N, typename Tin, int MODE>
-    int duo_cta(const b2s::StftArgs& a) {
-        using DP = b2s::DuoCtaPlan<LOG2N>;
-        return launch_any((const void*)b2s::stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
-                          stream);
-    }
-    template <typename Tin, int S, int MODE>
-    int duo(const b2s::StftArgs& a) {
-        using DP = b2s::DuoPlan;
-        return launch_any((const void*)b2s::stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
-    }
-    template <int LOG2N, typename Tin, int SHIFT, int MODE>
-    int warp(const b2s::StftArgs& a) {
-        using WP = b2s::WarpPlan<LOG2N>;
-#ifdef B2S_EXPERIMENTS
-        // A/B variants for tuning runs (B2S_VARIANT=n python tools/microbench.py ...)
-        if constexpr ((LOG2N == 9 || LOG2N == 10) && SHIFT == 4 && MODE == 0 && sizeof(Tin) == 4) {
-            const char* v = getenv("B2S_VARIANT");
-            const int vi = v ? atoi(v) : 0;
-            if (vi == 3) {
-                using W2 = b2s::WarpPlan<LOG2N, 128>;
-                return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE, 128, 4>,
-                                  W2::NT, W2::SMEM, W2::FPC, a, stream);
-            }
-        }
-#endif
-        return launch_any((const void*)b2s::stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>, WP::NT, WP::SMEM,
-                          WP::FPC, a, stream);
-    }
-    template <int LOG2N, typename Tin, int MODE>
-    int cta(const b2s::StftArgs& a) {
-        using PL = b2s::Plan<LOG2N>;
-        constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
-        return launch_any((const void*)b2s::stft_psd_kernel<LOG2N, Tin, MINB, MODE>, PL::NT, PL::SMEM, PL::FPC,
-                          a, stream);
-    }
-};
-
 template <typename Tin>
 int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
                const float* window, int detrend, double scale, int out_mode, float db_floor, int kmin,
@@ -224,14 +171,26 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
         if (rc < 0) return fail(rc, err);
     }
     if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
-    CudaLauncher L{(cudaStream_t)stream};
+    b2s::CudaLauncher L{(cudaStream_t)stream};
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
-    return b2s::dispatch_stft(a, L);
+    // the reference's call (linear power, every bin) takes the branch-free epilogue
+    const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
+    const int mode = a.band_mode ? b2s::EPI_BAND : (general ? b2s::EPI_GENERAL : b2s::EPI_PLAIN);
+    if (sizeof(Tin) == 8) {
+        if (mode == b2s::EPI_BAND) return b2s::dispatch_f64_band(a, L);
+        return mode == b2s::EPI_GENERAL ? b2s::dispatch_f64_general(a, L) : b2s::dispatch_f64_plain(a, L);
+    }
+    if (mode == b2s::EPI_BAND) return b2s::dispatch_f32_band(a, L);
+    return mode == b2s::EPI_GENERAL ? b2s::dispatch_f32_general(a, L) : b2s::dispatch_f32_plain(a, L);
 }
 
 }  // namespace
+
+int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream) {
+    return launch_any_impl(kern, nt, smem, fpc, a, stream);
+}
 
 extern "C" {
 

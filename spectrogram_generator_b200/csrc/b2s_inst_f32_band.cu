@@ -1,0 +1,6 @@
+// kernel instantiations: float samples, EPI_BAND epilogue (see b2s_launcher.hpp)
+#include "b2s_launcher.hpp"
+
+namespace b2s {
+int dispatch_f32_band(const StftArgs& a, CudaLauncher& L) { return dispatch_tg<float, EPI_BAND>(a, L); }
+}  // namespace b2s

@@ -1,0 +1,6 @@
+// kernel instantiations: double samples, EPI_PLAIN epilogue (see b2s_launcher.hpp)
+#include "b2s_launcher.hpp"
+
+namespace b2s {
+int dispatch_f64_plain(const StftArgs& a, CudaLauncher& L) { return dispatch_tg<double, EPI_PLAIN>(a, L); }
+}  // namespace b2s

@@ -346,85 +346,4 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     }
 }
 
-// ---- deterministic sum over the batch axis (cross-sweep mean) ----
-// in: [batch][elems] (row stride in_stride), out[slab][elems] partial sums over
-// a slab of rows; a second launch with batch = n_slabs folds the partials.
-B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stride, int batch,
-                                 int rows_per_slab, long long elems, float* __restrict__ out,
-                                 float post_scale) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // the last slabs are the rows the STFT kernel wrote last: take them first, while they are
-    // still in L2
-    const int slab = (int)(gridDim.y - 1 - blockIdx.y);
-    if (e >= elems) return;
-    const int r0 = slab * rows_per_slab;
-    const int r1 = (r0 + rows_per_slab < batch) ? r0 + rows_per_slab : batch;
-    const float* q = in + (long long)r0 * in_stride + e;
-    float a[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) a[j] = 0.f;
-    int r = r0;
-    for (; r + 16 <= r1; r += 16) {       // 16 independent loads in flight per thread
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] += q[j * in_stride];
-        q += 16 * in_stride;
-    }
-    for (; r < r1; ++r) { a[0] += q[0]; q += in_stride; }
-#pragma unroll
-    for (int w = 8; w >= 1; w >>= 1)
-#pragma unroll
-        for (int j = 0; j < w; ++j) a[j] += a[j + w];
-    out[(long long)slab * elems + e] = a[0] * post_scale;
-}
-
-
-// ---- display scaling (PlotEngine._plot_spectrogram, PlotEngine.py:126-131) -----------------
-// Sxx_norm = clip(S / (base + 1e-20), 0, 1), base = max(S) unless a positive global_max is
-// given; with log_scale: 10*log10(Sxx_norm + 1e-12), nan_to_num, min-max to [0, 1] (zeros if
-// the dB range is <= 1e-6).  min/max of the dB image follow from min/max of S (monotone), so
-// one reduction pass + one elementwise pass suffice.  S >= 0, so float bits order like uints.
-B2S_GLOBAL void minmax_init_kernel(unsigned* mm) {
-    mm[0] = 0u;             // max
-    mm[1] = 0x7f800000u;    // min (+inf)
-}
-
-B2S_GLOBAL void minmax_kernel(const float* __restrict__ s, long long elems, unsigned* mm) {
-    float mx = 0.f, mn = __uint_as_float(0x7f800000u);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems;
-         i += (long long)gridDim.x * blockDim.x) {
-        const float v = fmaxf(s[i], 0.f);        // NaN / negative -> 0, like the reference's clip
-        mx = fmaxf(mx, v);
-        mn = fminf(mn, v);
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(mm, __float_as_uint(mx));
-        atomicMin(mm + 1, __float_as_uint(mn));
-    }
-}
-
-B2S_DEVICE float display_norm(float v, float inv_base) { return fminf(fmaxf(v * inv_base, 0.f), 1.f); }
-
-B2S_GLOBAL void display_scale_kernel(const float* __restrict__ s, long long elems, const unsigned* mm, int log_scale,
-                                     float global_max, float* __restrict__ out) {
-    const float base = (global_max > 0.f) ? global_max : __uint_as_float(mm[0]);
-    const float inv_base = 1.0f / (base + 1e-20f);
-    float lo = 0.f, inv_range = 0.f;
-    if (log_scale) {
-        const float hi = 10.0f * log10f(display_norm(__uint_as_float(mm[0]), inv_base) + 1e-12f);
-        lo = 10.0f * log10f(display_norm(__uint_as_float(mm[1]), inv_base) + 1e-12f);
-        inv_range = (hi - lo > 1e-6f) ? 1.0f / (hi - lo) : 0.f;
-    }
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < elems;
-         i += (long long)gridDim.x * blockDim.x) {
-        float v = display_norm(s[i], inv_base);
-        if (log_scale) v = (10.0f * log10f(v + 1e-12f) - lo) * inv_range;
-        out[i] = v;
-    }
-}
-
 }  // namespace b2s

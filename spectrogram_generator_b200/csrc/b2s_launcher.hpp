@@ -1,0 +1,67 @@
+// The launcher the C-ABI entries hand to b2s::dispatch_tg, shared by the translation units the
+// kernel instantiations are spread over (b2s_inst_*.cu: one (sample type, epilogue mode) each,
+// compiled in parallel; b2s_api.cu holds the ABI, the caches and b2s_launch_any).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "b2s_dispatch.hpp"
+
+// One launch of an STFT kernel of any family: persistent grid sized from the occupancy, work
+// units sized from the grid (b2s::plan_stft).  Defined in b2s_api.cu.
+int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream);
+
+namespace b2s {
+
+struct CudaLauncher {
+    cudaStream_t stream;
+    bool allow_duo = true;
+    bool duo1024 = true;
+    bool allow_duo4 = true;
+    template <typename Tin, int S, int MODE>
+    int duo256(const StftArgs& a) {
+        using DP = Duo256Plan;
+        return b2s_launch_any((const void*)stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
+    }
+    template <int LOG2N, typename Tin, int S, int MODE>
+    int duo4(const StftArgs& a) {
+        using DP = Duo4Plan<LOG2N>;
+        return b2s_launch_any((const void*)stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
+                          stream);
+    }
+    template <int LOG2N, typename Tin, int MODE>
+    int duo_cta(const StftArgs& a) {
+        using DP = DuoCtaPlan<LOG2N>;
+        return b2s_launch_any((const void*)stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
+                          stream);
+    }
+    template <typename Tin, int S, int MODE>
+    int duo(const StftArgs& a) {
+        using DP = DuoPlan;
+        return b2s_launch_any((const void*)stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
+    }
+    template <int LOG2N, typename Tin, int SHIFT, int MODE>
+    int warp(const StftArgs& a) {
+        using WP = WarpPlan<LOG2N>;
+        return b2s_launch_any((const void*)stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>, WP::NT, WP::SMEM,
+                          WP::FPC, a, stream);
+    }
+    template <int LOG2N, typename Tin, int MODE>
+    int cta(const StftArgs& a) {
+        using PL = Plan<LOG2N>;
+        constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
+        return b2s_launch_any((const void*)stft_psd_kernel<LOG2N, Tin, MINB, MODE>, PL::NT, PL::SMEM, PL::FPC,
+                          a, stream);
+    }
+};
+
+
+// dispatch_tg<Tin, MODE> instantiated in b2s_inst_*.cu
+int dispatch_f32_plain(const StftArgs& a, CudaLauncher& L);
+int dispatch_f32_general(const StftArgs& a, CudaLauncher& L);
+int dispatch_f32_band(const StftArgs& a, CudaLauncher& L);
+int dispatch_f64_plain(const StftArgs& a, CudaLauncher& L);
+int dispatch_f64_general(const StftArgs& a, CudaLauncher& L);
+int dispatch_f64_band(const StftArgs& a, CudaLauncher& L);
+
+}  // namespace b2s

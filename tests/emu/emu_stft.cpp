@@ -10,6 +10,7 @@ dim3_ blockDim;
 dim3_ gridDim;
 namespace emu { Cta* g_cta = nullptr; }
 
+#include "b2s_aux_kernels.cuh"
 #include "b2s_dispatch.hpp"
 
 using namespace b2s;
