@@ -85,8 +85,35 @@ std::map<const void*, KernelState> g_kern;     // guarded by g_mu
 
 // One launch of an STFT kernel (either family): persistent grid sized from the
 // occupancy, work units sized from the grid (b2s::plan_stft).
+// Work counters for the dynamically scheduled kernels: a ring of (next unit, CTAs done) pairs per
+// device, zero when idle (the last CTA of a launch re-arms its pair).  The ring is long enough
+// that a pair is not handed out again while a launch that uses it can still be in flight; if it
+// ever were, units would only be processed twice (the stores are idempotent), never skipped.
+constexpr int kWorkRing = 1024;
+std::map<int, int*> g_work;                    // guarded by g_mu
+std::map<int, unsigned> g_work_next;           // guarded by g_mu
+
+int work_counters(int dev, int** out) {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_work.find(dev);
+    if (it == g_work.end()) {
+        int* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, 2 * kWorkRing * sizeof(int));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(work counters)");
+        e = cudaMemset(d, 0, 2 * kWorkRing * sizeof(int));
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(e, "cudaMemset(work counters)");
+        }
+        it = g_work.emplace(dev, d).first;
+        g_work_next[dev] = 0;
+    }
+    *out = it->second + 2 * (g_work_next[dev]++ % kWorkRing);
+    return B2S_OK;
+}
+
 int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
-                    bool direct_table = false) {
+                    bool direct_table = false, bool dynamic = false) {
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
@@ -110,9 +137,16 @@ int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::S
     const long long resident_ctas = (long long)di.sm_count * occ;
     b2s::StftParams p{};
     std::string err;
-    rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err);
+    // small launches (less than ~4 duos per resident group) keep the static schedule: the two
+    // counter round trips cost more than any imbalance they could remove
+    dynamic = dynamic && (a.batch * a.nframes >= 8 * resident_ctas * fpc);
+    rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err, dynamic);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
+    if (dynamic) {
+        rc = work_counters(dev, &p.work);
+        if (rc != B2S_OK) return rc;
+    }
     rc = twiddles(dev, a.nperseg, direct_table, &p.tw);
     if (rc != B2S_OK) return rc;
     // persistent grid: never more CTAs than work
@@ -175,6 +209,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     // the reference's call (linear power, every bin) takes the branch-free epilogue
     const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
     const int mode = a.band_mode ? b2s::EPI_BAND : (general ? b2s::EPI_GENERAL : b2s::EPI_PLAIN);
@@ -188,8 +223,9 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
 
 }  // namespace
 
-int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream) {
-    return launch_any_impl(kern, nt, smem, fpc, a, stream);
+int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
+                   bool dynamic) {
+    return launch_any_impl(kern, nt, smem, fpc, a, stream, false, dynamic);
 }
 
 extern "C" {

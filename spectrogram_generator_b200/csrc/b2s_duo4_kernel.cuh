@@ -41,7 +41,7 @@ struct Duo4Plan {
     static constexpr int OFF_TW1 = OFF_WIN + 8 * G;
     static constexpr int OFF_BUF = OFF_TW1 + 8 * 16;
     static constexpr int OFF_RED = OFF_BUF + NSUB * BUF;
-    static constexpr int TOTAL = OFF_RED + FPC * 3 * RED;      // one float4 per reduction slot
+    static constexpr int TOTAL = OFF_RED + FPC * (3 * RED + 1);    // one float4 per reduction slot + the unit draw
     static constexpr size_t SMEM = (size_t)TOTAL * sizeof(float4);
     static_assert(R == 2 || R == 4 || R == 8, "four-step duo kernel: nperseg 1024, 2048, 4096");
     static_assert(PL::NS == 256 && PL::GF == R, "plan tables");
@@ -86,7 +86,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
     const int t = j & 15;                                // lane inside the sub-transform
     float4* const bufs = sm4 + DP::OFF_BUF + (grp * R) * DP::BUF;    // the duo's R buffers
     float4* const buf = bufs + s * DP::BUF;
-    float4* const red = sm4 + DP::OFF_RED + grp * 3 * DP::RED;
+    float4* const red = sm4 + DP::OFF_RED + grp * (3 * DP::RED + 1);
 
     // ---- constant tables, once per CTA; the PSD scale goes into the window ----
     {
@@ -116,7 +116,27 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
     epi.db = p.out_mode;
     epi.band = cmk(0.f, 0.f);
 
-    for (long long u = (long long)blockIdx.x * DP::FPC + grp; u < p.n_units; u += (long long)gridDim.x * DP::FPC) {
+    // work units: static round-robin over the grid, or (p.work) an atomic counter every duo draws
+    // from; the next draw is issued a whole unit ahead, so its latency is hidden
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if constexpr (G <= 32) {
+            if (j == 0) b0 = atomicAdd(p.work, 1);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+        } else {
+            int* const slot = reinterpret_cast<int*>(red + 3 * DP::RED);
+            if (j == 0) *slot = atomicAdd(p.work, 1);
+            b2s_bar_sync(grp + 1, G);
+            b0 = *slot;
+            b2s_bar_sync(grp + 1, G);
+        }
+        return (long long)b0;
+    };
+    long long u_next = dyn ? draw() : (long long)blockIdx.x * DP::FPC + grp;
+    while (u_next < p.n_units) {
+        const long long u = u_next;
+        u_next = dyn ? draw() : u + (long long)gridDim.x * DP::FPC;
         const long long b = u / p.units_per_signal;
         const int c = (int)(u - b * p.units_per_signal);
         const int f_begin = c * p.chunk_frames;
@@ -295,6 +315,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
                     ob[f] = bs.x;
                     if (epi.actB) ob[f + 1] = bs.y;
                 }
+            }
+        }
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
             }
         }
     }

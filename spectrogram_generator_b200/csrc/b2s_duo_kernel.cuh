@@ -185,8 +185,19 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
     const bool is0 = (t == 0);
     const float edge = is0 ? 0.5f : 1.0f;                // DC / Nyquist carry scale, not 2 scale
 
+    // work units: static round-robin over the grid, or (p.work) an atomic counter the warps draw
+    // 2 units at a time from -- the next draw is issued a whole unit ahead, so its latency is hidden
     const long long ustride = (long long)gridDim.x * DP::FPC;
-    for (long long ub = (long long)blockIdx.x * DP::FPC + (grp & ~1); ub < p.n_units; ub += ustride) {
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if ((tid & 31) == 0) b0 = atomicAdd(p.work, 2);
+        return (long long)__shfl_sync(0xffffffffu, b0, 0);
+    };
+    long long ub_next = dyn ? draw() : (long long)blockIdx.x * DP::FPC + (grp & ~1);
+    while (ub_next < p.n_units) {
+        const long long ub = ub_next;
+        ub_next = dyn ? draw() : ub + ustride;
         long long u = ub + (grp & 1);
         const bool uvalid = u < p.n_units;
         if (!uvalid) u = p.n_units - 1;
@@ -383,6 +394,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
                     if (actA) ob[f] = band.x;
                     if (actB) ob[f + 1] = band.y;
                 }
+            }
+        }
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
             }
         }
     }

@@ -119,7 +119,7 @@ inline int validate_args(const StftArgs& a, std::string& err) {
 }
 
 inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_groups, StftParams& p,
-                     std::string& err) {
+                     std::string& err, bool dynamic = false) {
     const int log2n = ilog2_exact(a.nperseg);
     const int vrc = validate_args(a, err);
     if (vrc != B2S_OK) return vrc;
@@ -135,6 +135,7 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     p.out_batch_stride = a.out_batch_stride;
     p.window = a.window;
     p.tw = nullptr;
+    p.work = nullptr;
     p.out = a.out;
     p.nframes = (int)a.nframes;
     p.hop = a.hop;
@@ -150,7 +151,8 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     p.vec_ok = (base_ok && (a.hop % 2 == 0) && (a.x_batch_stride % 2 == 0 || a.batch <= 1)) ? 1 : 0;
     // work units: runs of consecutive frames of one signal
     long long total = a.batch * a.nframes;
-    long long want_units = resident_groups * 4;
+    // static round-robin: ~4 units per resident group; dynamic (atomic counter): ~6 smaller ones
+    long long want_units = resident_groups * (dynamic ? 6 : 4);
     long long cf = (want_units > 0) ? (total + want_units - 1) / want_units : a.nframes;
     if (cf < 1) cf = 1;
     if (cf > 64) cf = 64;

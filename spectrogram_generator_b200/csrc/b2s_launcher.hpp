@@ -9,7 +9,9 @@
 
 // One launch of an STFT kernel of any family: persistent grid sized from the occupancy, work
 // units sized from the grid (b2s::plan_stft).  Defined in b2s_api.cu.
-int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream);
+// `dynamic`: the kernel draws its work units from an atomic counter (StftParams::work).
+int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
+                   bool dynamic = false);
 
 namespace b2s {
 
@@ -18,16 +20,18 @@ struct CudaLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    bool dynamic_units = true;       // duo / duo256 / duo4 kernels: atomic work counter instead of static round-robin
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs& a) {
         using DP = Duo256Plan;
-        return b2s_launch_any((const void*)stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
+        return b2s_launch_any((const void*)stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream,
+                              dynamic_units);
     }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const StftArgs& a) {
         using DP = Duo4Plan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
-                          stream);
+                              stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs& a) {
@@ -38,7 +42,8 @@ struct CudaLauncher {
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs& a) {
         using DP = DuoPlan;
-        return b2s_launch_any((const void*)stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream);
+        return b2s_launch_any((const void*)stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream,
+                              dynamic_units);
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs& a) {

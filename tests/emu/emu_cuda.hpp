@@ -122,6 +122,12 @@ inline T __ldg(const T* p) { return *p; }
 
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline int atomicAdd(int* a, int v) {
+    std::lock_guard<std::mutex> g(emu::g_cta->mu);
+    const int old = *a;
+    *a = old + v;
+    return old;
+}
 inline unsigned atomicMax(unsigned* a, unsigned v) {
     std::lock_guard<std::mutex> g(emu::g_cta->mu);
     const unsigned old = *a;

@@ -21,17 +21,23 @@ struct EmuLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    bool dynamic_units = true;
+    int work[2] = {0, 0};
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs&) {
         using DP = Duo256Plan;
-        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo256_kernel<Tin, S, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo256_kernel<Tin, S, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;      // the last CTA re-armed the counters
     }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const StftArgs&) {
         using DP = Duo4Plan<LOG2N>;
-        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs&) {
@@ -42,8 +48,10 @@ struct EmuLauncher {
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs&) {
         using DP = DuoPlan;
-        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_kernel<Tin, S, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_kernel<Tin, S, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs&) {
@@ -96,6 +104,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
 

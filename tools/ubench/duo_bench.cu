@@ -28,7 +28,13 @@ void run(const char* name, K kern, int nt, size_t smem, int fpc, Ctx& c, int ite
     StftParams p{};
     std::string err;
     const long long resident = (long long)c.sms * occ;
-    if (plan_stft(c.a, fpc, resident * fpc, p, err) < 0) { printf("plan: %s\n", err.c_str()); exit(1); }
+    const bool dynamic = getenv("DYN") && atoi(getenv("DYN"));
+    if (plan_stft(c.a, fpc, resident * fpc, p, err, dynamic) < 0) { printf("plan: %s\n", err.c_str()); exit(1); }
+    if (dynamic) {
+        static int* work = nullptr;
+        if (!work) { CK(cudaMalloc(&work, 8)); CK(cudaMemset(work, 0, 8)); }
+        p.work = work;
+    }
     if (const char* cf = getenv("CHUNK")) {
         p.chunk_frames = atoi(cf);
         p.units_per_signal = (c.a.nframes + p.chunk_frames - 1) / p.chunk_frames;
