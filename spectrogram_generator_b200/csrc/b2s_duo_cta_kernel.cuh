@@ -53,7 +53,7 @@ struct DuoCtaPlan {
     // shared memory: [window M float2][FPC * BUF float4][FPC * 3 * RED float2 reduction slots]
     static constexpr size_t OFF_BUF = (size_t)M * sizeof(float2);
     static constexpr size_t OFF_RED = OFF_BUF + (size_t)FPC * BUF * sizeof(float4);
-    static constexpr size_t SMEM = OFF_RED + (size_t)FPC * 3 * RED * sizeof(float2);
+    static constexpr size_t SMEM = OFF_RED + (size_t)FPC * (3 * RED + 1) * sizeof(float2);   // + the unit draw
     static_assert(G >= 32 && G <= 128, "duo CTA kernel: nperseg 1024 .. 4096");
     static_assert(PL::P == 2, "two radix-16 passes");
 };
@@ -137,7 +137,7 @@ stft_psd_duo_cta_kernel(const StftParams p) {
     const unsigned lane = (unsigned)tid & 31u;
     float2* const swin = reinterpret_cast<float2*>(smem_raw);
     float4* const buf = reinterpret_cast<float4*>(smem_raw + DP::OFF_BUF) + (size_t)grp * DP::BUF;
-    float2* const red = reinterpret_cast<float2*>(smem_raw + DP::OFF_RED) + grp * 3 * DP::RED;
+    float2* const red = reinterpret_cast<float2*>(smem_raw + DP::OFF_RED) + grp * (3 * DP::RED + 1);
 
     // window (times sqrt(scale/2): |2 X|^2 is then the PSD of an interior bin), once per CTA
     {
@@ -159,7 +159,27 @@ stft_psd_duo_cta_kernel(const StftParams p) {
     epi.db = p.out_mode;
     epi.band = cmk(0.f, 0.f);
 
-    for (long long u = (long long)blockIdx.x * DP::FPC + grp; u < p.n_units; u += (long long)gridDim.x * DP::FPC) {
+    // work units: static round-robin over the grid, or (p.work) an atomic counter every duo draws
+    // from; the next draw is issued a whole unit ahead, so its latency is hidden
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if constexpr (G <= 32) {
+            if (j == 0) b0 = atomicAdd(p.work, 1);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+        } else {
+            int* const slot = reinterpret_cast<int*>(red + 3 * DP::RED);
+            if (j == 0) *slot = atomicAdd(p.work, 1);
+            b2s_bar_sync(grp + 1, G);
+            b0 = *slot;
+            b2s_bar_sync(grp + 1, G);
+        }
+        return (long long)b0;
+    };
+    long long u_next = dyn ? draw() : (long long)blockIdx.x * DP::FPC + grp;
+    while (u_next < p.n_units) {
+        const long long u = u_next;
+        u_next = dyn ? draw() : u + (long long)gridDim.x * DP::FPC;
         const long long b = u / p.units_per_signal;
         const int c = (int)(u - b * p.units_per_signal);
         const int f_begin = c * p.chunk_frames;
@@ -325,6 +345,16 @@ stft_psd_duo_cta_kernel(const StftParams p) {
                     ob[f] = bs.x;
                     if (actB) ob[f + 1] = bs.y;
                 }
+            }
+        }
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
             }
         }
     }

@@ -37,7 +37,7 @@ struct CudaLauncher {
     int duo_cta(const StftArgs& a) {
         using DP = DuoCtaPlan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
-                          stream);
+                              stream, dynamic_units);
     }
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs& a) {

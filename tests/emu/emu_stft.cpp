@@ -42,8 +42,10 @@ struct EmuLauncher {
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs&) {
         using DP = DuoCtaPlan<LOG2N>;
-        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, DP::NT, DP::SMEM, [&] { stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs&) {
