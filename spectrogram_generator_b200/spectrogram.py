@@ -351,6 +351,20 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
         else:
             fstep = max(1, _PIPE_CHUNK_BYTES // (kout * 4))
             items = [(b, b + 1, f, min(F, f + fstep)) for b in range(B) for f in range(0, F, fstep)]
+        if len(items) == 1:
+            # one stage: nothing to overlap -- copy in, compute, copy out on the caller's stream
+            x_d.copy_(h_in, non_blocking=pinned)
+            eng.stft_psd(x_d, plan, out=S_d, kmin=kmin, kmax=kmax, out_mode=out_mode, db_floor=db_floor)
+            if per_sweep:
+                h_out.copy_(S_d, non_blocking=True)
+            total = eng.batch_sum(S_d, sum_scale) if want_sum else None
+            cur.synchronize()
+            S = None
+            if per_sweep:
+                S = h_out.numpy()
+                if S.dtype != out_dtype:
+                    S = S.astype(out_dtype)
+            return S, total
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
         for (b0, b1, f0, f1) in items:

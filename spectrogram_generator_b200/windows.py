@@ -60,12 +60,35 @@ def _tukey(M, alpha, sym):
     return w if sym else w[:-1]
 
 
+_WINDOW_CACHE = {}
+
+
 def get_window(window, nperseg: int) -> np.ndarray:
     """float64 window of length ``nperseg`` == ``scipy.signal.get_window(window,
     nperseg)`` (fftbins=True; ``_periodic``/``_symmetric`` suffixes honoured,
-    _windows.py:2556-2561)."""
+    _windows.py:2556-2561).  Named windows are cached (read-only arrays): the reference
+    calls the path with the same (window, nperseg) for every sweep it plots."""
     if not (isinstance(nperseg, (int, np.integer)) and nperseg > 0):
         raise ValueError(f"Parameter Nx={nperseg} is not a positive integer")
+    if isinstance(window, (str, tuple)):
+        try:
+            key = (window, int(nperseg))
+            hit = _WINDOW_CACHE.get(key)
+        except TypeError:                    # unhashable tuple entries: SciPy will reject them below
+            key, hit = None, None
+        if hit is not None:
+            return hit
+        w = _get_window_uncached(window, nperseg)
+        if key is not None:
+            if len(_WINDOW_CACHE) > 256:
+                _WINDOW_CACHE.clear()
+            w.setflags(write=False)
+            _WINDOW_CACHE[key] = w
+        return w
+    return _get_window_uncached(window, nperseg)
+
+
+def _get_window_uncached(window, nperseg: int) -> np.ndarray:
     if not isinstance(window, (str, tuple)):
         from scipy.signal import get_window as _gw      # float -> kaiser(beta), as SciPy does
         return np.asarray(_gw(window, int(nperseg)), dtype=np.float64)
