@@ -1,0 +1,87 @@
+"""Every kernel family through the device API (Engine.stft_psd -> C ABI), seeded random shapes:
+parity with the oracle, bit-identity of frame-range sub-calls / strided batches / float64
+samples with the full float32 call, bin crop, dB, band power.  The families and the shapes
+that select them are listed in csrc/b2s_dispatch.hpp."""
+import numpy as np
+import pytest
+import torch
+
+import spectrogram_generator_b200 as sg
+from oracle import stft_oracle
+from util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+# (nperseg, hop) -> family that runs it
+CASES = [
+    (512, 128), (512, 64), (512, 256),                    # frame-duo kernel
+    (256, 64), (256, 32), (256, 128),                     # frame-duo kernel, 8 lanes
+    (1024, 256), (1024, 128), (1024, 512),                # four-step duo, R = 2
+    (2048, 512), (2048, 1024), (4096, 1024), (4096, 512), # four-step duo, R = 4 / 8
+    (1024, 896), (2048, 333), (4096, 3584),               # duo CTA kernel (reference default overlap, odd hop)
+    (512, 448), (256, 37), (128, 32), (64, 16),           # warp kernel
+    (8192, 2048), (16384, 4096),                          # three-pass CTA kernel
+    (1000, 875), (600, 150),                              # direct DFT
+]
+
+
+def _signal(rng, B, n, dc):
+    t = np.arange(n)
+    x = 0.3 * rng.standard_normal((B, n)) + np.sin(2 * np.pi * 0.0371 * t) + 0.5 * np.sin(2 * np.pi * 0.21 * t + 1.0) + dc
+    return x.astype(np.float32)
+
+
+@pytest.mark.parametrize("nperseg,hop", CASES)
+def test_family(nperseg, hop):
+    rng = np.random.default_rng(nperseg * 31 + hop)
+    B = int(rng.integers(1, 4))
+    nfr = int(rng.integers(5, 12))
+    n = nperseg + hop * (nfr - 1) + int(rng.integers(0, hop))
+    detrend = "constant" if rng.random() < 0.7 else False
+    window = ("tukey", .25) if rng.random() < 0.5 else "hann"
+    x = _signal(rng, B, n, dc=float(rng.choice([0.0, -3.0, 40.0])) if detrend else 0.0)
+    kw = dict(window=window, nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = sg.triage(n, 5000.0, window, nperseg, nperseg - hop, None, detrend, True, "density", "psd")
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=5000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    full = eng.stft_psd(xd, plan).cpu().numpy()
+    assert_parity(full, So, what=f"{nperseg}/{hop} {kw}")
+    # float64 samples holding the same values: same arithmetic, same bits
+    assert np.array_equal(eng.stft_psd(xd.double(), plan).cpu().numpy(), full)
+    # a strided batch (rows of a wider, 16-byte aligned buffer)
+    wide = torch.zeros((B, n + 8), dtype=torch.float32, device="cuda")
+    wide[:, :n] = xd
+    assert np.array_equal(eng.stft_psd(wide[:, :n], plan).cpu().numpy(), full)
+    # frame range + bin crop: bit-identical to the slice of the full result
+    K = nperseg // 2 + 1
+    k0, k1 = int(rng.integers(0, K // 3)), int(rng.integers(2 * K // 3, K))
+    part = eng.stft_psd(xd, plan, kmin=k0, kmax=k1, frame0=1, nframes=nfr - 2).cpu().numpy()
+    assert np.array_equal(part, full[:, 1:nfr - 1, k0:k1 + 1])
+    # dB with a floor
+    floor = float(1e-6 * So.max())
+    db = eng.stft_psd(xd, plan, out_mode=1, db_floor=floor).cpu().numpy()
+    ref_db = 10.0 * np.log10(np.maximum(So, floor))
+    big = So >= floor
+    assert np.max(np.abs(db[big] - ref_db[big])) <= 1e-3
+    # fused band power == sum of the cropped bins
+    band = eng.band_power(xd, plan, k0, k1).cpu().numpy()
+    np.testing.assert_allclose(band, full[:, :, k0:k1 + 1].astype(np.float64).sum(axis=-1), rtol=3e-6)
+
+
+@pytest.mark.parametrize("nperseg,hop", [(512, 128), (256, 64), (1024, 256), (2048, 512), (1024, 896)])
+def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg, hop):
+    """Enough work for the atomic work counter (b2s_api.cu: launch_any_impl): two launches give the
+    same bits, and every row equals the one-signal call (which takes the static schedule)."""
+    rng = np.random.default_rng(nperseg + hop)
+    B, n = 2000, nperseg + hop * 40
+    x = torch.from_numpy(_signal(rng, B, n, dc=1.0)).cuda()
+    plan = sg.triage(n, 1.0, "hann", nperseg, nperseg - hop, None, "constant", True, "density", "psd")
+    eng = sg.engine()
+    a = eng.stft_psd(x, plan)
+    b = eng.stft_psd(x, plan)
+    assert torch.equal(a, b)
+    for row in (0, 777, B - 1):
+        assert torch.equal(eng.stft_psd(x[row:row + 1], plan)[0], a[row])
