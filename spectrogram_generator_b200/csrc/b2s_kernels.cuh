@@ -64,7 +64,7 @@ struct Plan {
     static constexpr int TPT = (NS / 2) / G;                     // final tasks per thread
     static constexpr int BUF = M + (M >> 4) * 2;                 // padded complex slots
     static constexpr int RED = (G > 32) ? G / 32 : 1;            // mean partials per group
-    static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * 3 * RED * sizeof(float);
+    static constexpr size_t SMEM = (size_t)FPC * BUF * sizeof(float2) + (size_t)FPC * (3 * RED + 1) * sizeof(float);
     // constant tables (complex entries, W = exp(-2 pi i ./.)), laid out so that
     // consecutive lanes read consecutive entries:
     //   P1  [15][16]    W_256^(r jm)           pass 1 (P >= 2)
@@ -187,7 +187,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     const int grp = tid / G;
     const int j = tid - grp * G;
     float2* const buf = reinterpret_cast<float2*>(smem_raw) + (size_t)grp * PL::BUF;
-    float* const red = reinterpret_cast<float*>(smem_raw + (size_t)PL::FPC * PL::BUF * sizeof(float2)) + grp * 3 * PL::RED;
+    float* const red = reinterpret_cast<float*>(smem_raw + (size_t)PL::FPC * PL::BUF * sizeof(float2)) + grp * (3 * PL::RED + 1);
     const unsigned lane = (unsigned)tid & 31u;
     const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(unsigned)(G - 1)));
 
@@ -205,7 +205,27 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
     epi.kmax = p.kmax;
     epi.db = p.out_mode;
 
-    for (long long u = (long long)blockIdx.x * PL::FPC + grp; u < p.n_units; u += (long long)gridDim.x * PL::FPC) {
+    // work units: static round-robin over the grid, or (p.work) an atomic counter every group draws
+    // from; the next draw is issued a whole unit ahead, so its latency is hidden
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if constexpr (G <= 32) {
+            if (j == 0) b0 = atomicAdd(p.work, 1);
+            b0 = __shfl_sync(gmask, b0, (int)(lane & ~(unsigned)(G - 1)));
+        } else {
+            int* const slot = reinterpret_cast<int*>(red + 3 * PL::RED);
+            if (j == 0) *slot = atomicAdd(p.work, 1);
+            group_sync<G>(gmask, grp);
+            b0 = *slot;
+            group_sync<G>(gmask, grp);
+        }
+        return (long long)b0;
+    };
+    long long u_next = dyn ? draw() : (long long)blockIdx.x * PL::FPC + grp;
+    while (u_next < p.n_units) {
+        const long long u = u_next;
+        u_next = dyn ? draw() : u + (long long)gridDim.x * PL::FPC;
         const long long b = u / p.units_per_signal;
         const int c = (int)(u - b * p.units_per_signal);
         const int f_begin = c * p.chunk_frames;
@@ -343,6 +363,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Plan<LOG2N>::NT, MINB) stft_psd_kernel(const S
                     for (int w = 0; w < PL::RED; ++w) bs += red[2 * PL::RED + w];
                 }
                 if (j == 0) p.out[b * p.out_batch_stride + f] = bs;
+            }
+        }
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
             }
         }
     }

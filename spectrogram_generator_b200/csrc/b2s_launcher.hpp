@@ -20,7 +20,7 @@ struct CudaLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
-    bool dynamic_units = true;       // duo / duo256 / duo4 kernels: atomic work counter instead of static round-robin
+    bool dynamic_units = true;       // all FFT kernel families: atomic work counter instead of static round-robin (large launches)
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs& a) {
         using DP = Duo256Plan;
@@ -49,14 +49,14 @@ struct CudaLauncher {
     int warp(const StftArgs& a) {
         using WP = WarpPlan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>, WP::NT, WP::SMEM,
-                          WP::FPC, a, stream);
+                              WP::FPC, a, stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int cta(const StftArgs& a) {
         using PL = Plan<LOG2N>;
         constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
         return b2s_launch_any((const void*)stft_psd_kernel<LOG2N, Tin, MINB, MODE>, PL::NT, PL::SMEM, PL::FPC,
-                          a, stream);
+                              a, stream, dynamic_units);
     }
 };
 

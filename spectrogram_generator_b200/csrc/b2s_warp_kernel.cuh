@@ -133,8 +133,19 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
     epi.db = p.out_mode;
 
     const long long ustride = (long long)gridDim.x * WP::FPC;
-    // warp-uniform: the first group of a warp has the smallest unit index of the warp
-    for (long long ub = (long long)blockIdx.x * WP::FPC + (grp - (grp % WP::GW)); ub < p.n_units; ub += ustride) {
+    // work units: static round-robin over the grid (warp-uniform: the first group of a warp has the
+    // smallest unit index of the warp), or (p.work) an atomic counter the warps draw GW units at a
+    // time from -- the next draw is issued a whole unit ahead, so its latency is hidden
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if ((tid & 31) == 0) b0 = atomicAdd(p.work, WP::GW);
+        return (long long)__shfl_sync(0xffffffffu, b0, 0);
+    };
+    long long ub_next = dyn ? draw() : (long long)blockIdx.x * WP::FPC + (grp - (grp % WP::GW));
+    while (ub_next < p.n_units) {
+        const long long ub = ub_next;
+        ub_next = dyn ? draw() : ub + ustride;
         long long u = ub + (grp % WP::GW);
         const bool uvalid = u < p.n_units;
         if (!uvalid) u = p.n_units - 1;
@@ -277,6 +288,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(NT, MINB) stft_psd_warp_kernel(const StftParam
 #pragma unroll
                 for (int o = G / 2; o >= 1; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
                 if (j == 0 && act) p.out[b * p.out_batch_stride + f] = bs;
+            }
+        }
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
             }
         }
     }

@@ -58,14 +58,18 @@ struct EmuLauncher {
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs&) {
         using WP = WarpPlan<LOG2N>;
-        emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     template <int LOG2N, typename Tin, int MODE>
     int cta(const StftArgs&) {
         using PL = Plan<LOG2N>;
-        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, Tin, 1, MODE>(p); });
-        return 0;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, PL::NT, PL::SMEM, [&] { stft_psd_kernel<LOG2N, Tin, 1, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
 };
 
