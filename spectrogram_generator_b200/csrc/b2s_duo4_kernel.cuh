@@ -42,7 +42,13 @@ struct Duo4Plan {
     static constexpr int OFF_BUF = OFF_TW1 + 8 * 16;
     static constexpr int OFF_RED = OFF_BUF + NSUB * BUF;
     static constexpr int TOTAL = OFF_RED + FPC * (3 * RED + 1);    // one float4 per reduction slot + the unit draw
-    static constexpr size_t SMEM = (size_t)TOTAL * sizeof(float4);
+    // final-stage twiddles W_M^(r kap), W_N^k (float2 units after the float4 region) for R <= 4: they
+    // are read once per task and frame, so their L1 latency is exposed.  For R = 8 the extra 30 KB
+    // would leave too little L1 for the strided sample loads (measured: 4096/1024 0.59 -> 0.72 ms).
+    static constexpr bool POST_IN_SMEM = (R <= 4);
+    static constexpr int FIN2 = POST_IN_SMEM ? (R - 1) * 256 : 0;
+    static constexpr int POST2 = POST_IN_SMEM ? (M + 2) : 0;
+    static constexpr size_t SMEM = (size_t)TOTAL * sizeof(float4) + (size_t)(FIN2 + POST2) * sizeof(float2);
     static_assert(R == 2 || R == 4 || R == 8, "four-step duo kernel: nperseg 1024, 2048, 4096");
     static_assert(PL::NS == 256 && PL::GF == R, "plan tables");
 };
@@ -87,9 +93,22 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
     float4* const bufs = sm4 + DP::OFF_BUF + (grp * R) * DP::BUF;    // the duo's R buffers
     float4* const buf = bufs + s * DP::BUF;
     float4* const red = sm4 + DP::OFF_RED + grp * (3 * DP::RED + 1);
+    float2* const stab = reinterpret_cast<float2*>(sm4 + DP::TOTAL);
+    auto fin = [&](int i) -> float2 {            // W_M^(r kap) at (r - 1) * 256 + kap
+        if constexpr (DP::POST_IN_SMEM) return stab[i];
+        else return __ldg(p.tw + PL::OFF_FIN + i);
+    };
+    auto post = [&](int k) -> float2 {           // W_N^k
+        if constexpr (DP::POST_IN_SMEM) return stab[DP::FIN2 + k];
+        else return __ldg(p.tw + PL::OFF_POST + k);
+    };
 
     // ---- constant tables, once per CTA; the PSD scale goes into the window ----
     {
+        if constexpr (DP::POST_IN_SMEM) {
+            for (int i = tid; i < DP::FIN2; i += DP::NT) stab[i] = __ldg(p.tw + PL::OFF_FIN + i);
+            for (int i = tid; i <= M; i += DP::NT) stab[DP::FIN2 + i] = __ldg(p.tw + PL::OFF_POST + i);
+        }
         const float csc = sqrtf(0.5f * p.scale);
         const float2* w2 = reinterpret_cast<const float2*>(p.window);
         for (int i = tid; i < 8 * G; i += DP::NT) {
@@ -271,15 +290,15 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
                     }
 #pragma unroll
                     for (int r = 1; r < R; ++r) {
-                        U[r] = c2mul(U[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * 256 + kap));
-                        V[r] = c2mul(V[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * 256 + kap2));
+                        U[r] = c2mul(U[r], fin((r - 1) * 256 + kap));
+                        V[r] = c2mul(V[r], fin((r - 1) * 256 + kap2));
                     }
                     SmallFft2<R>::run(U);
                     SmallFft2<R>::run(V);
 #pragma unroll
                     for (int a = 0; a < R; ++a) {
                         const int k = kap + a * 256;
-                        epi.pair(k, M - k, U[a], V[R - 1 - a], __ldg(p.tw + PL::OFF_POST + k), 1.0f);
+                        epi.pair(k, M - k, U[a], V[R - 1 - a], post(k), 1.0f);
                     }
                 } else {
                     // kappa = 0 and kappa = 128 are their own mirrors (thread 0 of the duo)
@@ -290,13 +309,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
                         V[r] = cpx2{cmk(qb.x, qb.y), cmk(qb.z, qb.w)};
                     }
 #pragma unroll
-                    for (int r = 1; r < R; ++r) V[r] = c2mul(V[r], __ldg(p.tw + PL::OFF_FIN + (r - 1) * 256 + 128));
+                    for (int r = 1; r < R; ++r) V[r] = c2mul(V[r], fin((r - 1) * 256 + 128));
                     SmallFft2<R>::run(U);
                     SmallFft2<R>::run(V);
                     epi.pair(0, M, U[0], U[0], cmk(1.f, 0.f), 0.5f);           // DC / Nyquist carry scale, not 2 scale
 #pragma unroll
                     for (int a = 1; 2 * a < R; ++a)
-                        epi.pair(a * 256, M - a * 256, U[a], U[R - a], __ldg(p.tw + PL::OFF_POST + a * 256), 1.0f);
+                        epi.pair(a * 256, M - a * 256, U[a], U[R - a], post(a * 256), 1.0f);
                     {                                                       // k = M/2: X = conj(Z)
                         const cpx2 z = U[R / 2];
                         epi.put(M / 2, pk_muls(pk_fma(z.re, z.re, pk_mul(z.im, z.im)), 4.0f));
@@ -304,7 +323,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
 #pragma unroll
                     for (int a = 0; 2 * a < R - 1; ++a) {
                         const int k = 128 + a * 256;
-                        epi.pair(k, M - k, V[a], V[R - 1 - a], __ldg(p.tw + PL::OFF_POST + k), 1.0f);
+                        epi.pair(k, M - k, V[a], V[R - 1 - a], post(k), 1.0f);
                     }
                 }
             }
