@@ -42,10 +42,11 @@ struct Duo4Plan {
     static constexpr int OFF_BUF = OFF_TW1 + 8 * 16;
     static constexpr int OFF_RED = OFF_BUF + NSUB * BUF;
     static constexpr int TOTAL = OFF_RED + FPC * (3 * RED + 1);    // one float4 per reduction slot + the unit draw
-    // final-stage twiddles W_M^(r kap), W_N^k (float2 units after the float4 region) for R <= 4: they
-    // are read once per task and frame, so their L1 latency is exposed.  For R = 8 the extra 30 KB
-    // would leave too little L1 for the strided sample loads (measured: 4096/1024 0.59 -> 0.72 ms).
-    static constexpr bool POST_IN_SMEM = (R <= 4);
+    // final-stage twiddles W_M^(r kap), W_N^k (float2 units after the float4 region) for R = 4: they
+    // are read once per task and frame, so their L1 latency is exposed (C3: +2 %).  For R = 8 the
+    // extra 30 KB would leave too little L1 for the strided sample loads (measured: 4096/1024 0.59 ->
+    // 0.72 ms); for R = 2 staging them only lengthens the prologue of small launches.
+    static constexpr bool POST_IN_SMEM = (R == 4);
     static constexpr int FIN2 = POST_IN_SMEM ? (R - 1) * 256 : 0;
     static constexpr int POST2 = POST_IN_SMEM ? (M + 2) : 0;
     static constexpr size_t SMEM = (size_t)TOTAL * sizeof(float4) + (size_t)(FIN2 + POST2) * sizeof(float2);
