@@ -182,6 +182,15 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # The all-reduce of the partial mean is issued in stream order after the cross-sweep sum.
+    # Diagnostics (measured on 2 GPUs, 200 steps: none 0.222 ms/step, sync 0.237, async 1.23 -- async
+    # NCCL kernels spin beside the persistent STFT grids of their peers; reserving SMs for them with
+    # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = none | sync | async.
+    mode = os.environ.get("B2S_BENCH_ALLREDUCE", "sync")
+    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "0")))
+    from spectrogram_generator_b200 import _lib
+    _lib.load().b2s_set_reserved_sms(reserve)
+
     x_host, kw = make_batch(seed_offset=rank)
     plan = sg.triage(NS, FS, kw["window"], kw["nperseg"], kw["noverlap"], None, "constant", True, "density", "psd")
     eng = sg.engine()
@@ -215,10 +224,12 @@ def run_gpu(args):
         eng.stft_psd(x, plan, out=S)
         k_ev[i][1].record()
         mean = eng.batch_sum(S, 1.0 / total_sweeps)
-        if world > 1:
+        if world > 1 and mode == "async":
             # the 318 KB all-reduce of step i runs on NCCL's stream beside the STFT of step i+1;
             # every one of them is waited for before the end event
             pending.append((dist.all_reduce(mean, async_op=True), mean))
+        elif world > 1 and mode == "sync":
+            dist.all_reduce(mean)
     for w, _ in pending:
         w.wait()
     end.record()
@@ -273,7 +284,7 @@ def run_gpu(args):
                        "frames_per_sweep": F, "bins": K,
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
-                                      "(async, overlapped with the next step's STFT, all waited for inside the timed region)"},
+                                      f"({mode}, in stream order after the cross-sweep sum, inside the timed region)"},
             "roofline": {"bound": "hbm", "kernel": "stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, packed fp32x2)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,

@@ -43,6 +43,12 @@ extern "C" {
 #define B2S_OUT_DB 1     /* 10*log10(max(S, db_floor)) */
 
 int b2s_version(void);
+
+/* Size the persistent grids of the STFT kernels for (SM count - n) SMs, so that kernels of other
+ * streams -- e.g. the NCCL all-reduce of the partial mean spectrogram -- find free CTA slots while
+ * a launch is running.  Process-wide; returns the previous value.  Default 0.  (No counterpart in
+ * the reference: it has no device or collective layer) */
+int b2s_set_reserved_sms(int n);
 const char* b2s_last_error(void);
 
 /* 1 if `nperseg` runs on the fused radix-16 Stockham kernels (powers of two in

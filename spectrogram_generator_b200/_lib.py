@@ -87,6 +87,7 @@ _BAND_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void
 # name -> (restype, argtypes); must list every symbol include/b2s.h declares
 SIGNATURES = {
     "b2s_version": (c_int, []),
+    "b2s_set_reserved_sms": (c_int, [c_int]),
     "b2s_last_error": (c_char_p, []),
     "b2s_nperseg_support": (c_int, [c_int]),
     "b2s_frame_count": (c_longlong, [c_longlong, c_int, c_int]),

@@ -3,6 +3,7 @@
 // per-(device, nperseg) twiddle tables.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -33,6 +34,7 @@ struct DeviceInfo {
 };
 
 std::mutex g_mu;
+std::atomic<int> g_reserved_sms{0};
 std::map<int, DeviceInfo> g_dev;
 std::map<std::pair<int, int>, float2*> g_tw;     // (device, +-nperseg) -> tables (negative: direct-DFT table)
 
@@ -134,7 +136,10 @@ int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::S
         }
         occ = ks.occ;
     }
-    const long long resident_ctas = (long long)di.sm_count * occ;
+    // b2s_set_reserved_sms(): leave a few SMs' worth of CTA slots to kernels of other streams (a
+    // collective that should run beside the persistent grid); 0 by default
+    const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
+    const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
     b2s::StftParams p{};
     std::string err;
     // small launches (less than ~4 duos per resident group) keep the static schedule: the two
@@ -231,6 +236,12 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
 extern "C" {
 
 int b2s_version(void) { return B2S_ABI_VERSION; }
+
+int b2s_set_reserved_sms(int n) {
+    const int old = g_reserved_sms.load();
+    g_reserved_sms.store(n < 0 ? 0 : n);
+    return old;
+}
 
 const char* b2s_last_error(void) { return g_err.c_str(); }
 
