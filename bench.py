@@ -185,8 +185,8 @@ def run_gpu(args):
     # The all-reduce of the partial mean is issued in stream order after the cross-sweep sum.
     # Diagnostics (measured on 2 GPUs, 200 steps: none 0.222 ms/step, sync 0.237, async 1.23 -- async
     # NCCL kernels spin beside the persistent STFT grids of their peers; reserving SMs for them with
-    # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = none | sync | async.
-    mode = os.environ.get("B2S_BENCH_ALLREDUCE", "sync")
+    # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = peer (default) | sync | async | none.
+    mode = os.environ.get("B2S_BENCH_ALLREDUCE", "peer")
     reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "0")))
     from spectrogram_generator_b200 import _lib
     _lib.load().b2s_set_reserved_sms(reserve)
@@ -198,12 +198,32 @@ def run_gpu(args):
     S = torch.empty((B, plan.nframes, plan.nbins), dtype=torch.float32, device=dev)
     total_sweeps = B * world
 
-    def step():
-        eng.stft_psd(x, plan, out=S)
+    # the mean all-reduce: one kernel over NVLink peer memory (distributed.PeerMeanReducer); NCCL if
+    # symmetric memory cannot be set up on this box (B2S_BENCH_ALLREDUCE=sync forces NCCL)
+    peer = None
+    if world > 1 and mode == "peer":
+        try:
+            from spectrogram_generator_b200.distributed import PeerMeanReducer
+            peer = PeerMeanReducer(plan.nframes * plan.nbins, dev)
+        except Exception as e:          # pragma: no cover
+            if rank == 0:
+                print(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            mode = "sync"
+    collective = {"peer": "b2s_peer_allreduce_f32 (one kernel over NVLink peer memory)", "sync": "NCCL all_reduce",
+                  "async": "NCCL all_reduce (async)", "none": "none"}[mode] if world > 1 else "none"
+
+    def reduce_mean():
+        if peer is not None:
+            eng.batch_sum(S, 1.0, out=peer.partial())
+            return peer.reduce(1.0 / total_sweeps)
         mean = eng.batch_sum(S, 1.0 / total_sweeps)      # partial mean of this rank's sweeps
-        if world > 1:
+        if world > 1 and mode == "sync":
             dist.all_reduce(mean)                        # sum of partial means == global mean
         return mean
+
+    def step():
+        eng.stft_psd(x, plan, out=S)
+        return reduce_mean()
 
     for _ in range(max(3, args.warmup)):
         mean = step()
@@ -223,13 +243,11 @@ def run_gpu(args):
         k_ev[i][0].record()
         eng.stft_psd(x, plan, out=S)
         k_ev[i][1].record()
-        mean = eng.batch_sum(S, 1.0 / total_sweeps)
         if world > 1 and mode == "async":
-            # the 318 KB all-reduce of step i runs on NCCL's stream beside the STFT of step i+1;
-            # every one of them is waited for before the end event
+            mean = eng.batch_sum(S, 1.0 / total_sweeps)
             pending.append((dist.all_reduce(mean, async_op=True), mean))
-        elif world > 1 and mode == "sync":
-            dist.all_reduce(mean)
+        else:
+            mean = reduce_mean()
     for w, _ in pending:
         w.wait()
     end.record()
@@ -284,7 +302,7 @@ def run_gpu(args):
                        "frames_per_sweep": F, "bins": K,
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
-                                      f"({mode}, in stream order after the cross-sweep sum, inside the timed region)"},
+                                      f"({collective}, in stream order after the cross-sweep sum, inside the timed region)"},
             "roofline": {"bound": "hbm", "kernel": "stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, packed fp32x2)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
@@ -292,7 +310,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "spectrogram_generator_b200.mean_spectrogram(x_pinned, return_per_sweep=True)"},
-            "gpu_launches": args.steps * 3,
+            "gpu_launches": args.steps * (3 + (1 if peer is not None else 0)),
             "clocks": sampler.summary(),
         }
         if cpu_v is not None:

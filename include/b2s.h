@@ -49,6 +49,18 @@ int b2s_version(void);
  * a launch is running.  Process-wide; returns the previous value.  Default 0.  (No counterpart in
  * the reference: it has no device or collective layer) */
 int b2s_set_reserved_sms(int n);
+
+/* One-shot all-reduce (sum) of `elems` floats over NVLink peer memory: every rank has written its
+ * partial into a buffer that is mapped into all peers (peer_bufs[r] = the address of rank r's
+ * partial in THIS process, e.g. from torch's symmetric-memory rendezvous), and owns a zero-
+ * initialised signal pad of at least 128 bytes mapped likewise (peer_pads[r]).  One launch per rank
+ * on `stream`: announce, wait for every peer's announcement, add the partials in rank order
+ * (bit-identical on all ranks), write post_scale * sum to `out`.  `epoch` starts at 1 and grows by
+ * one per call on every rank; the partials of odd and even epochs must live in different buffers.
+ * Used for the mean-spectrogram all-reduce; the reference has no counterpart. */
+int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
+                           int rank, unsigned int epoch, long long elems, float* out, float post_scale,
+                           void* stream);
 const char* b2s_last_error(void);
 
 /* 1 if `nperseg` runs on the fused radix-16 Stockham kernels (powers of two in

@@ -88,6 +88,8 @@ _BAND_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void
 SIGNATURES = {
     "b2s_version": (c_int, []),
     "b2s_set_reserved_sms": (c_int, [c_int]),
+    "b2s_peer_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_longlong, c_void_p, c_float,
+                                       c_void_p]),
     "b2s_last_error": (c_char_p, []),
     "b2s_nperseg_support": (c_int, [c_int]),
     "b2s_frame_count": (c_longlong, [c_longlong, c_int, c_int]),

@@ -316,6 +316,31 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
 }
 
 
+int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
+                           int rank, unsigned int epoch, long long elems, float* out, float post_scale, void* stream) {
+    if (!peer_bufs || !peer_pads || !out || world < 1 || world > 16 || rank < 0 || rank >= world || elems < 1)
+        return fail(B2S_ERR_BAD_ARG, "b2s_peer_allreduce_f32: bad argument");
+    b2s::PeerPtrs pp{};
+    int vec_ok = (reinterpret_cast<uintptr_t>(out) % 16 == 0) ? 1 : 0;
+    for (int r = 0; r < world; ++r) {
+        pp.buf[r] = reinterpret_cast<const float*>(peer_bufs[r]);
+        pp.pad[r] = reinterpret_cast<unsigned*>(peer_pads[r]) + (epoch & 1u) * 16u;
+        if (peer_bufs[r] % 16) vec_ok = 0;
+    }
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const int block = 256;
+    long long want = (elems + block - 1) / block;
+    const unsigned grid = (unsigned)(want < di.sm_count ? want : di.sm_count);     // all CTAs resident: they all wait
+    b2s::peer_allreduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out, post_scale,
+                                                                         vec_ok);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce_kernel launch");
+    return B2S_OK;
+}
+
 int b2s_display_scale_f32(const float* s, long long elems, int log_scale, float global_max, float* out,
                           unsigned int* scratch, void* stream) {
     if (!s || !out || !scratch || elems < 1) return fail(B2S_ERR_BAD_ARG, "b2s_display_scale_f32: bad argument");

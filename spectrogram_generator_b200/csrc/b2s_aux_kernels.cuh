@@ -38,6 +38,68 @@ B2S_GLOBAL void batch_sum_kernel(const float* __restrict__ in, long long in_stri
 }
 
 
+#ifndef B2S_EMU
+// ---- one-shot all-reduce of the partial mean spectrogram over NVLink peer memory ----------
+// Every rank has written its partial sum into its own symmetric buffer (mapped into every peer
+// by torch's symmetric-memory rendezvous).  One launch per rank: announce "my partial of this
+// epoch is complete" in every peer's signal pad, wait until every peer has announced in mine,
+// then read all partials straight from peer memory and add them in rank order -- the result is
+// bit-identical on every rank and from run to run.  The buffers alternate between two halves
+// (epoch parity), so one announcement per epoch is enough: a rank can only overwrite the half of
+// epoch e at epoch e + 2, which it reaches after every peer has announced epoch e + 1, i.e. has
+// finished reading epoch e.
+struct PeerPtrs {
+    const float* buf[16];       // this epoch's partial of every rank
+    unsigned* pad[16];          // every rank's signal pad, at the slot block of this epoch's parity
+};
+
+B2S_GLOBAL void peer_allreduce_kernel(const PeerPtrs pp, int world, int rank, unsigned epoch, long long elems,
+                                      float* __restrict__ out, float post_scale, int vec_ok) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+        __threadfence_system();
+        unsigned* dst = pp.pad[threadIdx.x] + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    }
+    if ((int)threadIdx.x < world) {
+        const unsigned* src = pp.pad[rank] + threadIdx.x;
+        unsigned v;
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if (++spins > (1LL << 24)) __trap();          // a peer never arrived: fail loudly instead of hanging
+        } while ((int)(v - epoch) < 0);
+    }
+    __syncthreads();
+    // peer memory is read with ld.cv (never from a stale L1 line), 16 bytes at a time when the
+    // buffers allow it, all ranks' loads in flight before the adds; the adds go in rank order
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long n4 = vec_ok ? elems / 4 : 0;
+    for (long long q = tid; q < n4; q += nth) {
+        float4 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (r < world) v[r] = __ldcv(reinterpret_cast<const float4*>(pp.buf[r]) + q);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (r < world) {
+                acc.x += v[r].x;
+                acc.y += v[r].y;
+                acc.z += v[r].z;
+                acc.w += v[r].w;
+            }
+        reinterpret_cast<float4*>(out)[q] = make_float4(acc.x * post_scale, acc.y * post_scale, acc.z * post_scale,
+                                                        acc.w * post_scale);
+    }
+    for (long long e = 4 * n4 + tid; e < elems; e += nth) {
+        float acc = 0.f;
+        for (int r = 0; r < world; ++r) acc += __ldcv(pp.buf[r] + e);
+        out[e] = acc * post_scale;
+    }
+}
+#endif
+
 // ---- display scaling (PlotEngine._plot_spectrogram, PlotEngine.py:126-131) -----------------
 // Sxx_norm = clip(S / (base + 1e-20), 0, 1), base = max(S) unless a positive global_max is
 // given; with log_scale: 10*log10(Sxx_norm + 1e-12), nan_to_num, min-max to [0, 1] (zeros if

@@ -134,3 +134,59 @@ def gather_slabs(local: torch.Tensor, counts, dst: int = 0, *, group=None):
     if counts[rk] > 0:
         dist.send(local.contiguous(), dst=dst, group=group)
     return None
+
+
+class PeerMeanReducer:
+    """The mean-spectrogram all-reduce as ONE kernel over NVLink peer memory instead of an NCCL
+    call: each rank's cross-sweep sum lands in a symmetric buffer (torch's symmetric-memory
+    rendezvous maps it into every peer), and ``b2s_peer_allreduce_f32`` announces, waits for the
+    peers' announcements and adds the partials in rank order straight from peer memory -- the
+    result is bit-identical on every rank.  For the [F, K] partial of config 2 (318 KB) this
+    replaces ~30 us of collective latency per step by one ~10 us launch.
+
+    Usage (every rank, same order):  ``r = PeerMeanReducer(F * K, device)``; per step
+    ``engine().batch_sum(S, 1.0, out=r.partial())`` then ``mean = r.reduce(1.0 / total_sweeps)``.
+    """
+
+    def __init__(self, elems: int, device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._ct = ctypes
+        self._lib = _lib.load()
+        self.elems = int(elems)
+        self.device = torch.device(device)
+        group = group if group is not None else dist.group.WORLD
+        self.stride = (self.elems + 3) // 4 * 4           # both halves 16-byte aligned: 128-bit peer loads
+        self.buf = symm_mem.empty(2 * self.stride, dtype=torch.float32, device=self.device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.world, self.rank = int(self.handle.world_size), int(self.handle.rank)
+        if self.world > 16:
+            raise _lib.B2SError("PeerMeanReducer supports up to 16 ranks")
+        self._bufs = [int(p) for p in self.handle.buffer_ptrs]
+        self._pads = (ctypes.c_ulonglong * self.world)(*[int(p) for p in self.handle.signal_pad_ptrs])
+        self.epoch = 0
+        self.handle.barrier()                  # pads and buffers exist on every rank before the first kernel
+
+    def partial(self) -> torch.Tensor:
+        """Where this rank writes its partial of the coming ``reduce`` call."""
+        par = (self.epoch + 1) & 1
+        return self.buf[par * self.stride:par * self.stride + self.elems]
+
+    def reduce(self, post_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sum of all ranks' partials times ``post_scale`` -> ``out`` (allocated if None).  Enqueued
+        on the current stream; must be called by every rank, in the same order."""
+        self.epoch += 1
+        par = self.epoch & 1
+        if out is None:
+            out = torch.empty(self.elems, dtype=torch.float32, device=self.device)
+        bufs = (self._ct.c_ulonglong * self.world)(*[b + 4 * par * self.stride for b in self._bufs])
+        with torch.cuda.device(self.device):
+            rc = self._lib.b2s_peer_allreduce_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
+                                                  out.data_ptr(), float(post_scale),
+                                                  torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "b2s_peer_allreduce_f32")
+        return out

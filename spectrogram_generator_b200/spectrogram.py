@@ -224,14 +224,18 @@ class Engine:
         _lib.check(rc, "b2s_display_scale_f32")
         return out
 
-    def batch_sum(self, s: torch.Tensor, post_scale: float = 1.0) -> torch.Tensor:
-        """Deterministic sum over dim 0 of a contiguous CUDA float32 [B, ...] tensor."""
+    def batch_sum(self, s: torch.Tensor, post_scale: float = 1.0, out: torch.Tensor = None) -> torch.Tensor:
+        """Deterministic sum over dim 0 of a contiguous CUDA float32 [B, ...] tensor (optionally
+        into ``out``: any contiguous CUDA float32 tensor with as many elements as one row)."""
         lib = _lib.load()
         if not s.is_cuda or s.dtype != torch.float32 or not s.is_contiguous() or s.dim() < 2:
             raise ValueError("batch_sum expects a contiguous CUDA float32 tensor [B, ...]")
         B = s.shape[0]
         elems = s[0].numel()
-        out = torch.empty(s.shape[1:], dtype=torch.float32, device=s.device)
+        if out is None:
+            out = torch.empty(s.shape[1:], dtype=torch.float32, device=s.device)
+        elif not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == elems):
+            raise ValueError("batch_sum: out must be a contiguous CUDA float32 tensor with one row's elements")
         ns = lib.b2s_batch_sum_scratch_elems(B, elems)
         scratch = torch.empty(ns, dtype=torch.float32, device=s.device) if ns else None
         with torch.cuda.device(s.device):

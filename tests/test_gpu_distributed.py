@@ -49,6 +49,21 @@ def _worker(rank, world, port, out_dir):
             fw, tw, Sw = sg.spectrogram(y, fs=fs3, **kw3)
             assert np.array_equal(full.cpu().numpy().T, Sw), "time-sharded != unsharded bits"
         assert np.array_equal(t_loc, sg.windows.time_axis(len(y), 2048, 1536, fs3)[f0:f0 + c])
+        # the mean all-reduce as one kernel over NVLink peer memory == NCCL's, on every rank, repeatedly
+        dev = torch.device("cuda", rank)
+        elems = 309 * 257
+        red = D.PeerMeanReducer(elems, dev)
+        g = torch.Generator(device="cpu").manual_seed(100 + rank)
+        for it in range(5):
+            part = torch.rand(elems, generator=g).to(dev) * (it + 1)
+            red.partial().copy_(part)
+            got = red.reduce(0.25)
+            ref = part.clone()
+            dist.all_reduce(ref)
+            torch.testing.assert_close(got, ref * 0.25, rtol=1e-6, atol=0)
+            both = [torch.empty_like(got) for _ in range(world)]
+            dist.all_gather(both, got)
+            assert all(torch.equal(both[0], b) for b in both), "peer all-reduce differs between ranks"
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
