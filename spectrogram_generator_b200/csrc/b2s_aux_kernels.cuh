@@ -66,7 +66,7 @@ B2S_GLOBAL void peer_allreduce_kernel(const PeerPtrs pp, int world, int rank, un
         long long spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if (++spins > (1LL << 24)) __trap();          // a peer never arrived: fail loudly instead of hanging
+            if (++spins > (1LL << 26)) __trap();          // a peer never arrived (~1 min): fail loudly instead of hanging
         } while ((int)(v - epoch) < 0);
     }
     __syncthreads();
