@@ -234,8 +234,10 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
             // x' = x - (coarse mean) is exact or nearly so whatever the DC level; the mean r of
             // x' is then removed inside the window multiply with a single rounding.
             // (Measured and lost on B200: removing r after pass 0 through the transformed taps,
-            //  and computing the next duo's pivots one iteration ahead -- both lengthen live
-            //  ranges at 160+ registers and add shared-memory reads; 4-7 % slower.)
+            //  computing the next duo's pivots one iteration ahead, and carrying per-hop-block
+            //  means / residual sums across duos so that no reduction precedes the transform
+            //  (fewer operations, no shuffle chain in front) -- all lengthen live ranges at the
+            //  168-register cap; 2-7 % slower.)
             cpx2 v[16];
             if (p.detrend) {
                 float cA, cB;
