@@ -182,6 +182,7 @@ int main(int argc, char** argv) {
     if (HOP == 128) {
         run("warp<9,float,4,0>", stft_psd_warp_kernel<9, float, 4, 0>, WP::NT, WP::SMEM, WP::FPC, c);
         run("duo<float,4,0>", stft_psd_duo_kernel<float, 4, 0, 3, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+        if (getenv("MINB2")) run("duo<float,4,0,MINB=2>", stft_psd_duo_kernel<float, 4, 0, 2, 0>, DP::NT, DP::SMEM, DP::FPC, c);
         run("duo OPT=8  no STG", stft_psd_duo_kernel<float, 4, 0, 3, 8>, DP::NT, DP::SMEM, DP::FPC, c);
         run("duo OPT=16 no exchange", stft_psd_duo_kernel<float, 4, 0, 3, 16>, DP::NT, DP::SMEM, DP::FPC, c);
         run("duo OPT=32 no mirror shfl", stft_psd_duo_kernel<float, 4, 0, 3, 32>, DP::NT, DP::SMEM, DP::FPC, c);
