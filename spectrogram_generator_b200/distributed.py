@@ -62,27 +62,33 @@ def _cuda_compute(x2d: np.ndarray, plan: Plan) -> torch.Tensor:
 
 def mean_spectrogram_sharded(x_local, total_sweeps: int, fs=1.0, window=("tukey", .25), nperseg=None,
                              noverlap=None, detrend="constant", scaling="density", *, group=None,
-                             compute: Optional[Compute] = None, return_local=False):
+                             compute: Optional[Compute] = None, return_local=False, reducer=None):
     """Cross-sweep mean with sweeps sharded over ranks.
 
     ``x_local[B_r, N]`` holds this rank's sweeps (``shard_rows``).  Each rank sums
-    its own spectrograms on the device, one ``all_reduce(SUM)`` of ``[F, K]`` fp32
-    follows, then the division by ``total_sweeps``.  Returns ``(f, t, Smean[K, F])``
-    as a torch tensor on the compute device (identical on every rank)."""
+    its own spectrograms on the device, one all-reduce (sum) of ``[F, K]`` fp32
+    follows, then the division by ``total_sweeps``.  The all-reduce is NCCL's, or --
+    with ``reducer=PeerMeanReducer(F * K, device)``, created once and reused -- one
+    kernel over NVLink peer memory.  Returns ``(f, t, Smean[K, F])`` as a torch
+    tensor on the compute device (identical on every rank)."""
     x_local = np.asarray(x_local)
     plan = triage(x_local.shape[-1], fs, window, nperseg, noverlap, None, detrend, True, scaling, "psd")
     compute = compute or _cuda_compute
     S = compute(x_local.reshape(-1, plan.n), plan) if x_local.shape[0] else None
     if S is None:
         raise ValueError("every rank needs at least one sweep")
-    if S.is_cuda:
-        part = engine().batch_sum(S, 1.0)
-    else:                                    # injected CPU compute (gloo tests)
-        part = S.sum(dim=0)
     ws, _ = world(group)
-    if ws > 1:
-        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
-    mean = part * (1.0 / float(total_sweeps))
+    if reducer is not None and S.is_cuda and ws > 1:
+        engine().batch_sum(S, 1.0, out=reducer.partial())
+        mean = reducer.reduce(1.0 / float(total_sweeps)).view(S.shape[1:])
+    else:
+        if S.is_cuda:
+            part = engine().batch_sum(S, 1.0)
+        else:                                    # injected CPU compute (gloo tests)
+            part = S.sum(dim=0)
+        if ws > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        mean = part * (1.0 / float(total_sweeps))
     f = rfftfreq(plan.nperseg, fs)
     t = time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
     out = (f, t, mean.transpose(-1, -2))

@@ -64,6 +64,10 @@ def _worker(rank, world, port, out_dir):
             both = [torch.empty_like(got) for _ in range(world)]
             dist.all_gather(both, got)
             assert all(torch.equal(both[0], b) for b in both), "peer all-reduce differs between ranks"
+        # ... and the same reducer behind the sharded mean
+        red2 = D.PeerMeanReducer(309 * 257, dev)
+        _, _, mean_p = D.mean_spectrogram_sharded(x[lo:hi], 37, fs=fs, reducer=red2, **kw)
+        assert np.max(np.abs(mean_p.cpu().numpy() - mo)) <= 1e-6 * mo.max()
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
