@@ -214,6 +214,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
     if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     // the reference's call (linear power, every bin) takes the branch-free epilogue
     const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;

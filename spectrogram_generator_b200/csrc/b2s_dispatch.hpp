@@ -12,6 +12,8 @@
 //   template <int LOG2N, typename Tin, int MODE>            int duo_cta(const StftArgs&);
 //   template <int LOG2N, typename Tin, int S, int MODE>     int duo4(const StftArgs&);
 //   template <typename Tin, int S, int MODE>                int duo256(const StftArgs&);
+//   template <int LOG2N, typename Tin, int MODE>            int big(const StftArgs&);   (8192, 16384)
+//   bool allow_big;
 //   bool allow_duo, duo1024, allow_duo4;
 //
 //   nperseg == 512 with hop in {64, 128, 256} (2-element aligned frames) takes the packed
@@ -24,6 +26,7 @@
 #pragma once
 
 #include "b2s_host.hpp"
+#include "b2s_big_kernel.cuh"
 #include "b2s_duo256_kernel.cuh"
 #include "b2s_duo4_kernel.cuh"
 #include "b2s_duo_cta_kernel.cuh"
@@ -127,8 +130,8 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
             return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
         case 11: return L.allow_duo ? dispatch_duo_big<11, Tin, MODE>(a, L) : L.template cta<11, Tin, MODE>(a);
         case 12: return L.allow_duo ? dispatch_duo_big<12, Tin, MODE>(a, L) : L.template cta<12, Tin, MODE>(a);
-        case 13: return L.template cta<13, Tin, MODE>(a);
-        case 14: return L.template cta<14, Tin, MODE>(a);
+        case 13: return L.allow_big ? L.template big<13, Tin, MODE>(a) : L.template cta<13, Tin, MODE>(a);
+        case 14: return L.allow_big ? L.template big<14, Tin, MODE>(a) : L.template cta<14, Tin, MODE>(a);
         default: return B2S_ERR_UNSUPPORTED;
     }
 }

@@ -20,6 +20,13 @@ struct CudaLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    bool allow_big = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int big(const StftArgs& a) {
+        using BP = BigPlan<LOG2N>;
+        return b2s_launch_any((const void*)stft_psd_big_kernel<LOG2N, Tin, MODE>, BP::NT, BP::SMEM, BP::FPC, a, stream,
+                              dynamic_units);
+    }
     bool dynamic_units = true;       // all FFT kernel families: atomic work counter instead of static round-robin (large launches)
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs& a) {

@@ -21,6 +21,7 @@ struct EmuLauncher {
     bool allow_duo = true;
     bool duo1024 = true;
     bool allow_duo4 = true;
+    bool allow_big = true;
     bool dynamic_units = true;
     int work[2] = {0, 0};
     template <typename Tin, int S, int MODE>
@@ -61,6 +62,14 @@ struct EmuLauncher {
         StftParams q = p;
         if (dynamic_units) q.work = work;
         emu::launch(grid, WP::NT, WP::SMEM, [&] { stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
+    }
+    template <int LOG2N, typename Tin, int MODE>
+    int big(const StftArgs&) {
+        using BP = BigPlan<LOG2N>;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        emu::launch(grid, BP::NT, BP::SMEM, [&] { stft_psd_big_kernel<LOG2N, Tin, MODE>(q); });
         return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     template <int LOG2N, typename Tin, int MODE>
@@ -110,6 +119,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
     if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
