@@ -212,17 +212,38 @@ def run_gpu(args):
     collective = {"peer": "b2s_peer_allreduce_f32 (one kernel over NVLink peer memory)", "sync": "NCCL all_reduce",
                   "async": "NCCL all_reduce (async)", "none": "none"}[mode] if world > 1 else "none"
 
+    # per-sweep spectrograms + cross-sweep sum: ONE kernel keeps the running sums on chip while it
+    # writes the rows (b2s_stft_psd_sum_f32), a 22-row fold finishes the sum.  B2S_BENCH_FUSED_SUM=0 runs
+    # the earlier two-kernel form (b2s_stft_psd_f32, then b2s_batch_sum_f32 reading all rows back).
+    fused = os.environ.get("B2S_BENCH_FUSED_SUM", "1") != "0"
+    mean_buf = torch.empty((plan.nframes, plan.nbins), dtype=torch.float32, device=dev)
+
+    def spectrograms():
+        """The STFT launch of the step; in the fused form it also leaves the (partial) sum."""
+        if not fused:
+            eng.stft_psd(x, plan, out=S)
+        elif peer is not None:
+            eng.stft_psd_sum(x, plan, out=S, sum_out=peer.partial())
+        else:
+            eng.stft_psd_sum(x, plan, post_scale=1.0 / total_sweeps, out=S, sum_out=mean_buf)
+
+    def partial_mean():
+        if fused:
+            return mean_buf
+        return eng.batch_sum(S, 1.0 / total_sweeps, out=mean_buf)
+
     def reduce_mean():
         if peer is not None:
-            eng.batch_sum(S, 1.0, out=peer.partial())
+            if not fused:
+                eng.batch_sum(S, 1.0, out=peer.partial())
             return peer.reduce(1.0 / total_sweeps)
-        mean = eng.batch_sum(S, 1.0 / total_sweeps)      # partial mean of this rank's sweeps
+        mean = partial_mean()                            # partial mean of this rank's sweeps
         if world > 1 and mode == "sync":
             dist.all_reduce(mean)                        # sum of partial means == global mean
         return mean
 
     def step():
-        eng.stft_psd(x, plan, out=S)
+        spectrograms()
         return reduce_mean()
 
     for _ in range(max(3, args.warmup)):
@@ -241,10 +262,10 @@ def run_gpu(args):
     pending = []
     for i in range(args.steps):
         k_ev[i][0].record()
-        eng.stft_psd(x, plan, out=S)
+        spectrograms()
         k_ev[i][1].record()
         if world > 1 and mode == "async":
-            mean = eng.batch_sum(S, 1.0 / total_sweeps)
+            mean = partial_mean().clone()
             pending.append((dist.all_reduce(mean, async_op=True), mean))
         else:
             mean = reduce_mean()
@@ -294,6 +315,13 @@ def run_gpu(args):
         peak, peak_src = hbm_peak()
         achieved = bytes_alg / (kern_ms * 1e-3) / 1e9
         cpu_v, cpu_cores, cpu_dt = cpu_baseline_leg(x_host, kw, all_cores=False) if world == 1 else (None, None, None)
+        if fused:
+            kernel_name = ("stft_psd_duo_sum_kernel<float,S=4> (nperseg 512, hop 128: two frames per lane group, packed "
+                           "fp32x2, walks a block of sweeps and keeps their running sum in shared memory); kernel_ms "
+                           "brackets this launch plus the ~5 us fold of its 22 partial sums")
+        else:
+            kernel_name = ("stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, "
+                           "packed fp32x2)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -303,14 +331,14 @@ def run_gpu(args):
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
                                       f"({collective}, in stream order after the cross-sweep sum, inside the timed region)"},
-            "roofline": {"bound": "hbm", "kernel": "stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, packed fp32x2)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel_ms": kern_ms, "frac_of_nominal_8000": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "spectrogram_generator_b200.mean_spectrogram(x_pinned, return_per_sweep=True)"},
-            "gpu_launches": args.steps * (3 + (1 if peer is not None else 0)),
+            "gpu_launches": args.steps * ((2 if fused else 3) + (1 if peer is not None else 0)),
             "clocks": sampler.summary(),
         }
         if cpu_v is not None:

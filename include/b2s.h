@@ -142,6 +142,31 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
                       float* out, float* scratch, float post_scale, void* stream);
 
 /*
+ * Per-sweep spectrograms AND their cross-sweep sum in one pass (BASELINE config 2:
+ * "per-sweep spectrograms + mean spectrogram").  Arguments as
+ * b2s_stft_psd_f32 with linear power and every bin; in addition
+ *
+ *   sum_out     device, [nframes][nperseg/2+1] fp32:
+ *               post_scale * sum_b out[b][frame][bin], added in a fixed order
+ *               (sweep order inside a block of sweeps, then block order)
+ *   scratch     device, b2s_stft_psd_sum_scratch_elems(batch, nframes*(nperseg/2+1)) floats
+ *
+ * For nperseg 512 with hop 64 / 128 / 256 one kernel walks a frame pair over a block of
+ * sweeps and keeps the running sums on chip, so the [batch][nframes][bins] result is written
+ * once and never read back; every other shape runs b2s_stft_psd_* followed by
+ * b2s_batch_sum_f32.  The per-sweep rows are bit-identical to b2s_stft_psd_*'s either way.
+ */
+long long b2s_stft_psd_sum_scratch_elems(long long batch, long long elems);
+int b2s_stft_psd_sum_f32(const float* x, long long batch, long long n, long long x_batch_stride,
+                         int nperseg, int hop, const float* window, int detrend, double scale,
+                         long long frame0, long long nframes, float* out, long long out_batch_stride,
+                         float* sum_out, float post_scale, float* scratch, void* stream);
+int b2s_stft_psd_sum_f64(const double* x, long long batch, long long n, long long x_batch_stride,
+                         int nperseg, int hop, const float* window, int detrend, double scale,
+                         long long frame0, long long nframes, float* out, long long out_batch_stride,
+                         float* sum_out, float post_scale, float* scratch, void* stream);
+
+/*
  * Display scaling of a (cropped) spectrogram on the device -- PlotEngine._plot_spectrogram,
  * PlotEngine.py:126-131: out = clip(S/(base+1e-20), 0, 1) with base = max(S) (or global_max
  * when > 0); with log_scale, 10*log10(out+1e-12) min-max normalised to [0,1] (zeros when the

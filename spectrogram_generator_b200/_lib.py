@@ -84,6 +84,9 @@ _STFT_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void
 _BAND_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_p, c_int, c_double,
               c_int, c_int, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p]
 
+_SUM_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_p, c_int, c_double,
+             c_longlong, c_longlong, c_void_p, c_longlong, c_void_p, c_float, c_void_p, c_void_p]
+
 # name -> (restype, argtypes); must list every symbol include/b2s.h declares
 SIGNATURES = {
     "b2s_version": (c_int, []),
@@ -97,6 +100,9 @@ SIGNATURES = {
     "b2s_stft_psd_f64": (c_int, _STFT_ARGS),
     "b2s_stft_band_power_f32": (c_int, _BAND_ARGS),
     "b2s_stft_band_power_f64": (c_int, _BAND_ARGS),
+    "b2s_stft_psd_sum_scratch_elems": (c_longlong, [c_longlong, c_longlong]),
+    "b2s_stft_psd_sum_f32": (c_int, _SUM_ARGS),
+    "b2s_stft_psd_sum_f64": (c_int, _SUM_ARGS),
     "b2s_batch_sum_scratch_elems": (c_longlong, [c_longlong, c_longlong]),
     "b2s_batch_sum_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p,
                                   c_float, c_void_p]),

@@ -13,6 +13,7 @@
 
 #include "../../include/b2s.h"
 #include "b2s_aux_kernels.cuh"
+#include "b2s_duo_sum_kernel.cuh"
 #include "b2s_launcher.hpp"
 
 namespace {
@@ -227,6 +228,84 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     return mode == b2s::EPI_GENERAL ? b2s::dispatch_f32_general(a, L) : b2s::dispatch_f32_plain(a, L);
 }
 
+constexpr int kMaxSumBlocks = 64;       // sweep blocks of the sum-fused kernel: bounds its scratch
+
+// the sum-fused frame-duo kernel (per-sweep rows and their cross-sweep sum in one pass), then the
+// fold over its sweep blocks.  Static schedule: plan_stft_sum makes the units fill the grid evenly.
+int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post_scale, float* scratch,
+                   cudaStream_t stream) {
+    using DP = b2s::DuoPlan;
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const void* kern = b2s::duo_sum_kernel_for(a.x_is_f64, slots);
+    if (!kern) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
+    const size_t smem = b2s::DuoSumPlan::SMEM;
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        KernelState& ks = g_kern[kern];
+        if (ks.dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, DP::NT, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            if (ks.occ < 1) ks.occ = 1;
+            ks.dev = dev;
+        }
+        occ = ks.occ;
+    }
+    const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
+    const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
+    b2s::StftParams p{};
+    std::string err;
+    const int blocks = b2s::plan_stft_sum(a, resident_ctas * DP::FPC, kMaxSumBlocks, p, err);
+    if (blocks < 0) return fail(blocks, err);
+    if (p.n_units == 0) return B2S_OK;
+    p.acc = scratch;
+    rc = twiddles(dev, a.nperseg, false, &p.tw);
+    if (rc != B2S_OK) return rc;
+    const long long need = (p.n_units + DP::FPC - 1) / DP::FPC;
+    const long long grid = (need < resident_ctas) ? need : resident_ctas;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)DP::NT), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sum-fused stft kernel launch");
+    const long long elems = a.nframes * (a.nperseg / 2 + 1);
+    const int block = 256;
+    b2s::batch_sum_kernel<<<dim3((unsigned)((elems + block - 1) / block), 1), block, 0, stream>>>(
+        scratch, elems, blocks, blocks, elems, sum_out, post_scale);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
+    return B2S_OK;
+}
+
+template <typename Tin>
+int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
+                          const float* window, int detrend, double scale, long long frame0, long long nframes,
+                          float* out, long long out_batch_stride, float* sum_out, float post_scale, float* scratch,
+                          void* stream) {
+    b2s::StftArgs a{x, (int)(sizeof(Tin) == 8), batch, n, x_batch_stride, nperseg, hop, window, detrend,
+                    scale, B2S_OUT_LINEAR, 0.f, 0, nperseg / 2, frame0, nframes, out, out_batch_stride, 0};
+    {
+        std::string err;
+        int rc = b2s::validate_args(a, err);
+        if (rc < 0) return fail(rc, err);
+    }
+    if (!sum_out || !scratch) return fail(B2S_ERR_BAD_ARG, "b2s_stft_psd_sum: sum_out and scratch are required");
+    if (nframes < 1 || batch < 1) return fail(B2S_ERR_BAD_ARG, "b2s_stft_psd_sum: nothing to sum");
+    const long long elems = nframes * (nperseg / 2 + 1);
+    const char* off = getenv("B2S_NO_FUSED_SUM");
+    const char* noduo = getenv("B2S_NO_DUO");
+    const int slots = ((off && atoi(off)) || (noduo && atoi(noduo)) || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
+    if (slots) return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
+    // every other shape: the per-sweep kernel of its family, then the two-pass sum
+    int rc = stft_entry<Tin>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR, 0.f, 0,
+                             nperseg / 2, frame0, nframes, out, out_batch_stride, stream);
+    if (rc != B2S_OK) return rc;
+    return b2s_batch_sum_f32(out, batch, elems, out_batch_stride, sum_out, scratch, post_scale, stream);
+}
+
 }  // namespace
 
 int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
@@ -314,6 +393,30 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
     return B2S_OK;
+}
+
+
+long long b2s_stft_psd_sum_scratch_elems(long long batch, long long elems) {
+    if (batch < 1 || elems < 1) return 0;
+    const long long fused = (batch < kMaxSumBlocks ? batch : kMaxSumBlocks) * elems;
+    const long long two_pass = b2s_batch_sum_scratch_elems(batch, elems);
+    return fused > two_pass ? fused : two_pass;
+}
+
+int b2s_stft_psd_sum_f32(const float* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
+                         const float* window, int detrend, double scale, long long frame0, long long nframes,
+                         float* out, long long out_batch_stride, float* sum_out, float post_scale, float* scratch,
+                         void* stream) {
+    return stft_sum_entry<float>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, frame0, nframes,
+                                 out, out_batch_stride, sum_out, post_scale, scratch, stream);
+}
+
+int b2s_stft_psd_sum_f64(const double* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
+                         const float* window, int detrend, double scale, long long frame0, long long nframes,
+                         float* out, long long out_batch_stride, float* sum_out, float post_scale, float* scratch,
+                         void* stream) {
+    return stft_sum_entry<double>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, frame0, nframes,
+                                  out, out_batch_stride, sum_out, post_scale, scratch, stream);
 }
 
 

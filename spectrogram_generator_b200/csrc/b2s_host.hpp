@@ -136,6 +136,9 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     p.window = a.window;
     p.tw = nullptr;
     p.work = nullptr;
+    p.acc = nullptr;
+    p.acc_rows = 0;
+    p.acc_batch = 0;
     p.out = a.out;
     p.nframes = (int)a.nframes;
     p.hop = a.hop;
@@ -163,6 +166,37 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     p.n_units = p.units_per_signal * a.batch;
     (void)groups_per_cta;
     return log2n;
+}
+
+// Work units of the sum-fused frame-duo kernel (b2s_duo_sum_kernel.cuh): a unit is one frame duo
+// over a block of `rows` consecutive sweeps, so every unit costs the same and the static
+// round-robin is balanced when the units fill the resident lane groups a whole number of times.
+// Fewest rounds x (rows + 1 for the start-up of a unit) wins, fewer blocks (less partial-sum
+// traffic) break ties.  Returns the number of blocks (<= max_blocks).
+inline int plan_stft_sum(const StftArgs& a, long long resident_groups, int max_blocks, StftParams& p,
+                         std::string& err) {
+    const int log2n = plan_stft(a, 1, resident_groups, p, err, false);
+    if (log2n < 0) return log2n;
+    const long long nduos = (a.nframes + 1) / 2, ups = (nduos + 1) / 2 * 2;
+    if (resident_groups < 1) resident_groups = 1;
+    long long best_cost = -1, best_rows = a.batch > 0 ? a.batch : 1;
+    for (long long nb = 1; nb <= max_blocks && nb <= a.batch; ++nb) {
+        const long long rows = (a.batch + nb - 1) / nb, blocks = (a.batch + rows - 1) / rows;
+        const long long rounds = (blocks * ups + resident_groups - 1) / resident_groups;
+        const long long cost = rounds * (rows + 1) * 4096 + blocks;
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best_rows = rows;
+        }
+    }
+    const long long blocks = a.batch > 0 ? (a.batch + best_rows - 1) / best_rows : 0;
+    p.acc = nullptr;
+    p.acc_rows = (int)best_rows;
+    p.acc_batch = (int)a.batch;
+    p.chunk_frames = 2;
+    p.units_per_signal = ups;
+    p.n_units = blocks * ups;
+    return (int)blocks;
 }
 
 #define B2S_DISPATCH_LOG2N(log2n, F)   \

@@ -38,6 +38,9 @@ struct StftParams {
     const float* window;         // [nperseg] fp32 window table, device
     const float2* tw;            // [Plan::TABLE] twiddle tables (see Plan), device
     float* out;                  // [batch][nframes][kmax-kmin+1]
+    float* acc;                  // fused cross-sweep sum (stft_psd_duo_sum_kernel): [blocks][nframes][bins] partials
+    int acc_rows;                // sweeps per block
+    int acc_batch;               // sweeps in the launch
     int* work;                   // dynamic unit scheduling (duo kernels): work[0] = next unit, work[1] = CTAs
                                  // done; both zero at launch, reset by the last CTA.  NULL: static round-robin
     int nframes;                 // frames per signal computed by this launch

@@ -68,6 +68,9 @@ struct CudaLauncher {
 };
 
 
+// the sum-fused frame-duo kernel for hop = slots * 32 (b2s_inst_sum.cu); nullptr if there is none
+const void* duo_sum_kernel_for(int x_is_f64, int slots);
+
 // dispatch_tg<Tin, MODE> instantiated in b2s_inst_*.cu
 int dispatch_f32_plain(const StftArgs& a, CudaLauncher& L);
 int dispatch_f32_general(const StftArgs& a, CudaLauncher& L);

@@ -65,27 +65,35 @@ def mean_spectrogram_sharded(x_local, total_sweeps: int, fs=1.0, window=("tukey"
                              compute: Optional[Compute] = None, return_local=False, reducer=None):
     """Cross-sweep mean with sweeps sharded over ranks.
 
-    ``x_local[B_r, N]`` holds this rank's sweeps (``shard_rows``).  Each rank sums
-    its own spectrograms on the device, one all-reduce (sum) of ``[F, K]`` fp32
-    follows, then the division by ``total_sweeps``.  The all-reduce is NCCL's, or --
+    ``x_local[B_r, N]`` holds this rank's sweeps (``shard_rows``).  Each rank computes
+    its spectrograms and their sum in one pass on the device, one all-reduce (sum) of
+    ``[F, K]`` fp32 follows, then the division by ``total_sweeps``.  The all-reduce is NCCL's, or --
     with ``reducer=PeerMeanReducer(F * K, device)``, created once and reused -- one
     kernel over NVLink peer memory.  Returns ``(f, t, Smean[K, F])`` as a torch
     tensor on the compute device (identical on every rank)."""
     x_local = np.asarray(x_local)
     plan = triage(x_local.shape[-1], fs, window, nperseg, noverlap, None, detrend, True, scaling, "psd")
-    compute = compute or _cuda_compute
-    S = compute(x_local.reshape(-1, plan.n), plan) if x_local.shape[0] else None
-    if S is None:
+    if x_local.shape[0] == 0:
         raise ValueError("every rank needs at least one sweep")
     ws, _ = world(group)
-    if reducer is not None and S.is_cuda and ws > 1:
-        engine().batch_sum(S, 1.0, out=reducer.partial())
-        mean = reducer.reduce(1.0 / float(total_sweeps)).view(S.shape[1:])
-    else:
-        if S.is_cuda:
-            part = engine().batch_sum(S, 1.0)
-        else:                                    # injected CPU compute (gloo tests)
-            part = S.sum(dim=0)
+    if compute is None:
+        # rows and this rank's partial sum in one pass (Engine.stft_psd_sum), straight into the
+        # reducer's symmetric buffer when there is one
+        eng = engine()
+        eng.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        use_peer = reducer is not None and ws > 1
+        S, part = eng.stft_psd_sum(_to_device(x_local.reshape(-1, plan.n), dev), plan,
+                                   sum_out=reducer.partial() if use_peer else None)
+        if use_peer:
+            mean = reducer.reduce(1.0 / float(total_sweeps)).view(S.shape[1:])
+        else:
+            if ws > 1:
+                dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+            mean = part * (1.0 / float(total_sweeps))
+    else:                                        # injected compute (the gloo tests run it on the CPU)
+        S = compute(x_local.reshape(-1, plan.n), plan)
+        part = engine().batch_sum(S, 1.0) if S.is_cuda else S.sum(dim=0)
         if ws > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
         mean = part * (1.0 / float(total_sweeps))
@@ -151,7 +159,8 @@ class PeerMeanReducer:
     replaces ~30 us of collective latency per step by one ~10 us launch.
 
     Usage (every rank, same order):  ``r = PeerMeanReducer(F * K, device)``; per step
-    ``engine().batch_sum(S, 1.0, out=r.partial())`` then ``mean = r.reduce(1.0 / total_sweeps)``.
+    ``engine().stft_psd_sum(x, plan, sum_out=r.partial())`` (or ``batch_sum(S, 1.0, out=r.partial())``)
+    then ``mean = r.reduce(1.0 / total_sweeps)``.
     """
 
     def __init__(self, elems: int, device, group=None):

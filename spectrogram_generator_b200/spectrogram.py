@@ -184,6 +184,57 @@ class Engine:
         _lib.check(rc, "b2s_stft_psd")
         return out
 
+    def stft_psd_sum(self, x: torch.Tensor, plan: Plan, *, post_scale: float = 1.0, out: torch.Tensor = None,
+                     sum_out: torch.Tensor = None):
+        """Per-sweep spectrograms and their cross-sweep sum in one pass (BASELINE config 2).
+        x: CUDA tensor [B, n]; returns ``(S[B, nframes, nbins], post_scale * S.sum(0))`` -- the
+        rows are bit-identical to :meth:`stft_psd`'s, the sum is added in a fixed order.  For the
+        shapes of the sum-fused kernel (nperseg 512, hop 64/128/256) the rows are written once and
+        never read back; other shapes run :meth:`stft_psd` followed by :meth:`batch_sum` inside
+        the library.  ``sum_out``: any contiguous CUDA float32 tensor of nframes*nbins elements."""
+        lib = _lib.load()
+        if x.dim() != 2 or not x.is_cuda or x.dtype not in (torch.float32, torch.float64):
+            raise ValueError("stft_psd_sum expects a CUDA float32/float64 tensor of shape [batch, n]")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        B, n = x.shape
+        if n != plan.n:
+            raise ValueError("plan was made for a different signal length")
+        if B == 0 or plan.nframes == 0:
+            raise ValueError("stft_psd_sum needs at least one sweep and one frame")
+        F, K = plan.nframes, plan.nbins
+        if out is None:
+            out = torch.empty((B, F, K), dtype=torch.float32, device=x.device)
+        elif out.shape != (B, F, K) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 [B, nframes, nbins] tensor")
+        if sum_out is None:
+            sum_out = torch.empty((F, K), dtype=torch.float32, device=x.device)
+        elif not (sum_out.is_cuda and sum_out.dtype == torch.float32 and sum_out.is_contiguous()
+                  and sum_out.numel() == F * K):
+            raise ValueError("sum_out must be a contiguous CUDA float32 tensor of nframes*nbins elements")
+        if lib.b2s_nperseg_support(plan.nperseg) == 0:
+            raise NotImplementedError(f"nperseg={plan.nperseg} is not supported by the B200 engine (1..16384)")
+        win = self.window_table(plan, x.device)
+        scratch = self._sum_scratch(lib.b2s_stft_psd_sum_scratch_elems(B, F * K), x.device)
+        fn = lib.b2s_stft_psd_sum_f32 if x.dtype == torch.float32 else lib.b2s_stft_psd_sum_f64
+        with torch.cuda.device(x.device):
+            rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
+                    plan.detrend, plan.scale, 0, F, out.data_ptr(), F * K, sum_out.data_ptr(), float(post_scale),
+                    scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_stft_psd_sum")
+        return out, sum_out
+
+    def _sum_scratch(self, elems: int, device) -> torch.Tensor:
+        """Partial-sum scratch of the sum-fused path, kept per device (stream-ordered reuse: the
+        kernels that touch it are enqueued on the caller's current stream)."""
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        cache = self.__dict__.setdefault("_scratch", {})
+        t = cache.get(key)
+        if t is None or t.numel() < elems:
+            t = torch.empty(max(int(elems), 1), dtype=torch.float32, device=device)
+            cache[key] = t
+        return t
+
     def band_power(self, x: torch.Tensor, plan: Plan, kmin: int, kmax: int, *, frame0=0, nframes=None) -> torch.Tensor:
         """Fused band-power feature: sum of bins kmin..kmax of every frame, CUDA float32
         [B, nframes]; the spectrogram itself is never written (PlotEngine.py:238-239)."""
@@ -358,10 +409,14 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
         if len(items) == 1:
             # one stage: nothing to overlap -- copy in, compute, copy out on the caller's stream
             x_d.copy_(h_in, non_blocking=pinned)
-            eng.stft_psd(x_d, plan, out=S_d, kmin=kmin, kmax=kmax, out_mode=out_mode, db_floor=db_floor)
+            if want_sum and kout == plan.nbins and out_mode == 0:
+                # rows and their cross-sweep sum in one pass (sum-fused kernel where there is one)
+                _, total = eng.stft_psd_sum(x_d, plan, post_scale=sum_scale, out=S_d)
+            else:
+                eng.stft_psd(x_d, plan, out=S_d, kmin=kmin, kmax=kmax, out_mode=out_mode, db_floor=db_floor)
+                total = eng.batch_sum(S_d, sum_scale) if want_sum else None
             if per_sweep:
                 h_out.copy_(S_d, non_blocking=True)
-            total = eng.batch_sum(S_d, sum_scale) if want_sum else None
             cur.synchronize()
             S = None
             if per_sweep:

@@ -12,6 +12,7 @@ namespace emu { Cta* g_cta = nullptr; }
 
 #include "b2s_aux_kernels.cuh"
 #include "b2s_dispatch.hpp"
+#include "b2s_duo_sum_kernel.cuh"
 
 using namespace b2s;
 
@@ -140,4 +141,55 @@ extern "C" int emu_batch_sum(const float* in, long long in_stride, int batch, in
         });
     }
     return 0;
+}
+
+// the sum-fused frame-duo kernel followed by the fold over its sweep blocks, planned by the library's
+// own plan_stft_sum with `grid` resident CTAs; returns the number of blocks (> 0) or an error (< 0)
+extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, long long n, long long x_batch_stride,
+                                int nperseg, int hop, const float* window, int detrend, double scale,
+                                long long frame0, long long nframes, float* out, long long out_batch_stride,
+                                float* sum_out, float post_scale, int grid, int max_blocks) {
+    StftArgs a{x, x_is_f64, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, 0,
+               0.f, 0, nperseg / 2, frame0, nframes, out, out_batch_stride, 0};
+    std::string err;
+    if (validate_args(a, err) < 0) return validate_args(a, err);
+    const int slots = duo_slots(a, ilog2_exact(nperseg));
+    if (!slots) return -200;
+    StftParams p{};
+    const int blocks = plan_stft_sum(a, (long long)grid * DuoPlan::FPC, max_blocks, p, err);
+    if (blocks < 0) return blocks;
+    std::vector<float> tw;
+    make_tables(nperseg, tw);
+    p.tw = reinterpret_cast<const float2*>(tw.data());
+    const long long elems = nframes * (nperseg / 2 + 1);
+    std::vector<float> part((size_t)blocks * elems, std::nanf(""));
+    p.acc = part.data();
+    const long long need = (p.n_units + DuoPlan::FPC - 1) / DuoPlan::FPC;
+    const unsigned g = (unsigned)(need < grid ? need : grid);
+    auto run = [&](auto kern) { emu::launch(g, DuoPlan::NT, DuoSumPlan::SMEM, [&] { kern(p); }); };
+    if (x_is_f64) {
+        if (slots == 2) run(stft_psd_duo_sum_kernel<double, 2>);
+        else if (slots == 4) run(stft_psd_duo_sum_kernel<double, 4>);
+        else run(stft_psd_duo_sum_kernel<double, 8>);
+    } else {
+        if (slots == 2) run(stft_psd_duo_sum_kernel<float, 2>);
+        else if (slots == 4) run(stft_psd_duo_sum_kernel<float, 4>);
+        else run(stft_psd_duo_sum_kernel<float, 8>);
+    }
+    emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
+    return blocks;
+}
+
+// plan_stft_sum alone: out = {sweeps per block, units per block, units}; returns the blocks
+extern "C" int emu_plan_sum(long long batch, long long nframes, long long resident_groups, int max_blocks, long long* out) {
+    static float dummy[4];
+    StftArgs a{dummy, 0, batch, 512 + 128 * (nframes - 1), 512 + 128 * (nframes - 1), 512, 128, dummy, 1, 1.0, 0,
+               0.f, 0, 256, 0, nframes, dummy, nframes * 257, 0};
+    StftParams p{};
+    std::string err;
+    const int blocks = plan_stft_sum(a, resident_groups, max_blocks, p, err);
+    out[0] = p.acc_rows;
+    out[1] = p.units_per_signal;
+    out[2] = p.n_units;
+    return blocks;
 }

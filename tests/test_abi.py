@@ -35,6 +35,11 @@ def test_host_only_entries():
     assert lib.b2s_frame_count(100, 512, 128) == 0
     assert lib.b2s_batch_sum_scratch_elems(1000, 79413) == 8 * 79413      # slabs of 128 sweeps
     assert lib.b2s_batch_sum_scratch_elems(128, 10) == 0
+    # the sum-fused call: up to 64 sweep blocks of partial sums, never less than the two-pass sum needs
+    assert lib.b2s_stft_psd_sum_scratch_elems(1000, 79413) == 64 * 79413
+    assert lib.b2s_stft_psd_sum_scratch_elems(3, 10) == 30
+    assert lib.b2s_stft_psd_sum_scratch_elems(20000, 10) == 157 * 10
+    assert lib.b2s_stft_psd_sum_scratch_elems(0, 10) == 0
 
 
 def test_bad_arguments_are_reported_before_any_device_work():

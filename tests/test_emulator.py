@@ -219,6 +219,46 @@ def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):
     np.testing.assert_allclose(edge, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
 
 
+@pytest.mark.parametrize("hop", [64, 128, 256])
+@pytest.mark.parametrize("nframes,batch,grid,max_blocks", [(7, 5, 1, 64), (6, 9, 2, 4), (1, 3, 1, 2), (5, 2, 3, 1)])
+def test_sum_fused_duo_kernel(emu, hop, nframes, batch, grid, max_blocks):
+    """The sum-fused frame-duo kernel (per-sweep rows + cross-sweep sum in one pass): the rows
+    are bit-identical to the per-sweep kernel's, the sum equals the float64 sum of the rows to
+    fp32 rounding, whatever the split into sweep blocks (odd duo counts leave a lane group idle,
+    odd frame counts a half-empty duo, the last block is ragged); float64 samples likewise."""
+    n = 512 + hop * (nframes - 1) + 4          # even: rows stay 8-byte aligned (else the library takes the two-pass path)
+    x = signal(batch, n, hop + nframes + batch, dc=-2.0)
+    kw = dict(window="hann", nperseg=512, noverlap=512 - hop)
+    plan = plan_for(n, 20000.0, **kw)
+    assert plan.nframes == nframes
+    rows = emu.stft_psd(x, plan, chunk=2)
+    got, tot, blocks = emu.stft_psd_sum(x, plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert 1 <= blocks <= min(max_blocks, batch)
+    assert np.array_equal(got, rows)
+    want = 0.5 * rows.astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(tot, want, rtol=1e-6, atol=0)
+    got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert np.array_equal(got64, rows) and np.array_equal(tot64, tot)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused duo 512/{hop}")
+
+
+def test_sum_fused_plan_fills_the_grid():
+    """plan_stft_sum on BASELINE config 2 with a B200's resident groups: one round, 22 blocks of 46."""
+    import ctypes
+    import __graft_entry__ as ge
+    lib = ctypes.CDLL(ge.build_emulator())
+    fn = lib.emu_plan_sum
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    o = (ctypes.c_longlong * 3)()
+    assert fn(1000, 309, 148 * 3 * 8, 64, o) == 22 and list(o) == [46, 156, 22 * 156]
+    assert fn(3, 309, 148 * 3 * 8, 64, o) == 3 and o[0] == 1
+    b = fn(1000, 100001, 148 * 3 * 8, 64, o)                # more duos than lane groups: few, long blocks
+    assert 1 <= b <= 16 and (b - 1) * o[0] < 1000 <= b * o[0]
+    assert fn(100000, 7, 148 * 3 * 8, 64, o) == 64
+
+
 @pytest.mark.parametrize("nperseg,hop", [(2048, 512), (2048, 333), (4096, 1024), (4096, 3584)])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):

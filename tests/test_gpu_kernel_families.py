@@ -85,3 +85,55 @@ def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg,
     assert torch.equal(a, b)
     for row in (0, 777, B - 1):
         assert torch.equal(eng.stft_psd(x[row:row + 1], plan)[0], a[row])
+
+
+@pytest.mark.parametrize("nperseg,hop,B,nfr,odd", [
+    (512, 128, 1000, 309, 0),       # BASELINE config 2: the sum-fused frame-duo kernel, one round of 22 blocks
+    (512, 128, 37, 10, 0), (512, 64, 5, 7, 0), (512, 256, 130, 6, 0), (512, 128, 2, 1, 0),
+    (512, 128, 9, 8, 1),            # odd row length: rows only 4-byte aligned -> two-pass path inside the library
+    (512, 128, 1, 12, 0),           # one sweep
+    (1024, 256, 40, 9, 0), (256, 64, 300, 11, 0), (600, 150, 7, 5, 0),       # no fused kernel for these shapes
+])
+def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
+    """Engine.stft_psd_sum (b2s_stft_psd_sum_f32/_f64): the rows are bit-identical to stft_psd's,
+    the sum equals the float64 sum of the rows to fp32 rounding and is the same on every run;
+    float64 samples and a caller-provided flat sum buffer likewise."""
+    rng = np.random.default_rng(nperseg + hop + B)
+    n = nperseg + hop * (nfr - 1) + (2 if not odd else 3)
+    x = _signal(rng, B, n, dc=-3.0)
+    plan = sg.triage(n, 20000.0, "hann", nperseg, nperseg - hop, None, "constant", True, "density", "psd")
+    assert plan.nframes == nfr
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    rows = eng.stft_psd(xd, plan)
+    S, tot = eng.stft_psd_sum(xd, plan, post_scale=1.0 / B)
+    assert torch.equal(S, rows)
+    want = rows.double().sum(dim=0) / B
+    torch.testing.assert_close(tot.double(), want, rtol=2e-6, atol=0)
+    flat = torch.full((nfr * plan.nbins,), float("nan"), device="cuda")
+    S2, tot2 = eng.stft_psd_sum(xd, plan, post_scale=1.0 / B, sum_out=flat)
+    assert tot2 is flat and torch.equal(flat.view(nfr, -1), tot) and torch.equal(S2, rows)
+    S3, tot3 = eng.stft_psd_sum(xd.double(), plan, post_scale=1.0 / B)
+    assert torch.equal(S3, rows) and torch.equal(tot3, tot)
+
+
+def test_fused_sum_matches_the_two_pass_sum_and_the_public_mean(monkeypatch):
+    """The sum-fused kernel against the earlier form (stft_psd, then batch_sum) on a C2-shaped batch,
+    and mean_spectrogram (which takes the fused call) against the oracle's float64 mean."""
+    from spectrogram_generator_b200 import synth
+    x, kw = synth.config2(batch=200)
+    fs = kw.pop("fs")
+    plan = sg.triage(x.shape[-1], fs, kw["window"], kw["nperseg"], kw["noverlap"], None, "constant", True,
+                     "density", "psd")
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    S, tot = eng.stft_psd_sum(xd, plan)
+    monkeypatch.setenv("B2S_NO_FUSED_SUM", "1")
+    S0, tot0 = eng.stft_psd_sum(xd, plan)
+    monkeypatch.delenv("B2S_NO_FUSED_SUM")
+    assert torch.equal(S, S0)
+    torch.testing.assert_close(tot, tot0, rtol=2e-6, atol=0)
+    assert torch.equal(tot0, eng.batch_sum(eng.stft_psd(xd, plan)))
+    f, t, m = sg.mean_spectrogram(x, fs=fs, **kw)
+    _, _, mo = stft_oracle.mean_spectrogram(x.astype(np.float64), fs=fs, **kw)
+    assert_parity(m, mo, what="mean spectrogram through the sum-fused kernel")

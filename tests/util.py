@@ -111,6 +111,25 @@ class Emulator:
         assert rc == 0, rc
         return out
 
+    def stft_psd_sum(self, x2d, plan, post_scale=1.0, grid=2, max_blocks=64):
+        """The sum-fused frame-duo kernel + fold: (rows[B, F, K], sum[F, K], blocks used)."""
+        x2d = np.ascontiguousarray(x2d)
+        B, n = x2d.shape
+        F, K = plan.nframes, plan.nbins
+        w = plan.win64.astype(np.float32)
+        out = np.full((B, F, K), np.nan, np.float32)
+        tot = np.full((F, K), np.nan, np.float32)
+        c = ctypes
+        fn = self.lib.emu_stft_psd_sum
+        fn.restype = c.c_int
+        fn.argtypes = [c.c_void_p, c.c_int, c.c_longlong, c.c_longlong, c.c_longlong, c.c_int, c.c_int, c.c_void_p,
+                       c.c_int, c.c_double, c.c_longlong, c.c_longlong, c.c_void_p, c.c_longlong, c.c_void_p,
+                       c.c_float, c.c_int, c.c_int]
+        rc = fn(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg, plan.hop, w.ctypes.data,
+                plan.detrend, plan.scale, 0, F, out.ctypes.data, F * K, tot.ctypes.data, post_scale, grid, max_blocks)
+        assert rc > 0, rc
+        return out, tot, rc
+
     def batch_sum(self, s, post_scale=1.0, rows_per_slab=64):
         s = np.ascontiguousarray(s, dtype=np.float32)
         B = s.shape[0]
