@@ -239,19 +239,26 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-    const void* kern = b2s::duo_sum_kernel_for(a.x_is_f64, slots);
-    if (!kern) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
+    const char* smem_acc = getenv("B2S_SUM_ACC_SMEM");
+    const int tmem = (smem_acc && atoi(smem_acc)) ? 0 : 1;
+    const void* twin = b2s::duo_sum_kernel_for(a.x_is_f64, slots, 0);
+    const void* kern = tmem ? b2s::duo_sum_kernel_for(a.x_is_f64, slots, 1) : twin;
+    if (!kern || !twin) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
     const size_t smem = b2s::DuoSumPlan::SMEM;
     int occ = 0;
     {
         std::lock_guard<std::mutex> g(g_mu);
         KernelState& ks = g_kern[kern];
         if (ks.dev != dev) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            // residency from the shared-memory twin (same registers bound, same shared memory): the
+            // query answers 1 for a kernel that allocates tensor memory
+            cudaError_t e = cudaFuncSetAttribute(twin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, DP::NT, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, twin, DP::NT, smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
             if (ks.occ < 1) ks.occ = 1;
+            if (ks.occ * b2s::DuoSumPlan::TMEM_COLS > 512) ks.occ = 512 / b2s::DuoSumPlan::TMEM_COLS;
             ks.dev = dev;
         }
         occ = ks.occ;

@@ -18,16 +18,46 @@
 
 namespace b2s {
 
+
+#ifndef B2S_EMU
+// Tensor memory as per-thread scratch (no tensor-core math involved): with the 32x32b shape a
+// thread reads / writes N consecutive 32-bit columns of its own TMEM lane (warp w of the CTA owns
+// lanes 32 (w % 4) ... + 31).  The accesses go over the tensor-memory datapath, not the L1 /
+// shared-memory data pipe the rest of the kernel keeps busy.
+__device__ __forceinline__ void tm_ld4(unsigned addr, float& a, float& b, float& c, float& d) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+__device__ __forceinline__ void tm_ld2(unsigned addr, float& a, float& b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr));
+}
+__device__ __forceinline__ void tm_ld_wait4(float& a, float& b, float& c, float& d) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b), "+f"(c), "+f"(d) : : "memory");
+}
+__device__ __forceinline__ void tm_ld_wait2(float& a, float& b) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b) : : "memory");
+}
+__device__ __forceinline__ void tm_st4(unsigned addr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 : : "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tm_st2(unsigned addr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" : : "r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" : : : "memory"); }
+#endif
+
 struct DuoSumPlan {
     static constexpr int ACC = 9 * DuoPlan::G;                          // float4 per duo
     static constexpr size_t SMEM = DuoPlan::SMEM + (size_t)DuoPlan::FPC * ACC * sizeof(float4);
+    static constexpr int TMEM_COLS = 64;                                // 34 used: 8 x (k: A, B; 256 - k: A, B) + bin 128
 };
 
 // units: (sweep block, duo) with the duo index fastest, so that the groups working at the same
 // time are on neighbouring frames of the same sweeps (their overlapping samples meet in L1 / L2).
 // p.units_per_signal = duos per block rounded up to even, p.n_units = blocks * that
 // (plan_stft_sum); p.acc_rows sweeps per block, p.acc_batch sweeps in all.
-template <typename Tin, int S>
+template <typename Tin, int S, int ACC_TMEM = 0>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_kernel(const StftParams p) {
     using DP = DuoPlan;
     using PL = Plan<9>;
@@ -54,14 +84,31 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
             const float2 ta = (j == 0) ? cmk(1.f, 0.f) : __ldg(p.tw + PL::OFF_P1 + (2 * j - 1) * 16 + l);
             const float2 tb = __ldg(p.tw + PL::OFF_P1 + (2 * j) * 16 + l);
             sm4[DP::OFF_TW1 + i] = make_float4(ta.x, ta.y, tb.x, tb.y);
-            if (j < 4) {
-                const float2 pa = __ldg(p.tw + PL::OFF_POST + l + 16 * (2 * j));
-                const float2 pb = __ldg(p.tw + PL::OFF_POST + l + 16 * (2 * j + 1));
-                sm4[DP::OFF_TWP + i] = make_float4(pa.x, pa.y, pb.x, pb.y);
-            }
+            // split twiddles as [pp][lane] float2: one conflict-free 64-bit read per pair (the
+            // [pp / 2][lane] float4 rows of the per-sweep kernel were re-read here half by half,
+            // 16 bytes apart: two-way bank conflicts, +5 % shared-memory wavefronts)
+            reinterpret_cast<float2*>(sm4 + DP::OFF_TWP)[i] = __ldg(p.tw + PL::OFF_POST + l + 16 * j);
         }
     }
+#ifndef B2S_EMU
+    unsigned tacc = 0;
+    if constexpr (ACC_TMEM) {
+        __shared__ unsigned tmem_base_s;
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         : : "r"((unsigned)__cvta_generic_to_shared(&tmem_base_s)), "n"(DuoSumPlan::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" : : : "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" : : : "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" : : : "memory");
+        tacc = tmem_base_s + ((unsigned)((tid >> 5) & 3) << 21);        // lane field: 32 (warp % 4) << 16
+    } else {
+        __syncthreads();
+    }
+#else
     __syncthreads();
+#endif
 
     const int partner = (tid & 16) | ((16 - t) & 15);
     const bool is0 = (t == 0);
@@ -102,8 +149,17 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
 #pragma unroll
         for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(xn + ((i < 16) ? 0 : offB) + 32 * i);
         // the block sums start at zero; only this lane touches its slots, no barrier needed
+#ifndef B2S_EMU
+        if constexpr (ACC_TMEM) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) sacc[j * G] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 8; ++j) tm_st4(tacc + 4 * j, 0.f, 0.f, 0.f, 0.f);
+            tm_st2(tacc + 32, 0.f, 0.f);
+        } else
+#endif
+        {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) sacc[j * G] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 
         for (int it = 0; it < ntrip; ++it) {
 
@@ -192,6 +248,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) {
                 const cpx2 zk = v[perm16(pp)];
+                float4 a4;
+#ifndef B2S_EMU
+                if constexpr (ACC_TMEM) {
+                    if (pp == 0) tm_st_wait();                         // the previous sweep's updates have landed
+                    tm_ld4(tacc + 4 * pp, a4.x, a4.y, a4.z, a4.w);     // in flight during the butterfly below
+                }
+#endif
                 // the mirror Z[256 - k] sits in the partner lane at p' = 15 - pp; lane 0 pairs
                 // k = 16 pp with 16 (16 - pp), which it holds itself (it is its own partner)
                 const cpx2 s15 = v[perm16(15 - pp)], s16 = v[perm16((16 - pp) & 15)];
@@ -200,8 +263,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
                 cpx2 zm;
                 zm.re = cmk(__shfl_sync(0xffffffffu, s0, partner), __shfl_sync(0xffffffffu, s1, partner));
                 zm.im = cmk(__shfl_sync(0xffffffffu, s2, partner), __shfl_sync(0xffffffffu, s3, partner));
-                const float4 w4 = sm4[DP::OFF_TWP + (pp >> 1) * 16 + t];
-                const float2 w = (pp & 1) ? cmk(w4.z, w4.w) : cmk(w4.x, w4.y);
+                const float2 w = reinterpret_cast<const float2*>(sm4 + DP::OFF_TWP)[pp * 16 + t];
                 const cpx2 e{pk_add(zk.re, zm.re), pk_sub(zk.im, zm.im)};      // 2E = zk + conj(zm)
                 const cpx2 o{pk_add(zk.im, zm.im), pk_sub(zm.re, zk.re)};      // 2O = -i (zk - conj(zm))
                 const cpx2 tw = c2mul(o, w);
@@ -220,8 +282,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
                     pA[KOUT + 16 * pp] = pk.y;
                     pmA[KOUT - 16 * pp] = pm.y;
                 }
-                {   // (34 more live registers do not fit beside the transform: measured with spills 2 % slower)
-                    const float4 a4 = sacc[pp * G];
+                // (34 more live registers do not fit beside the transform: measured with spills 2 % slower)
+#ifndef B2S_EMU
+                if constexpr (ACC_TMEM) {
+                    tm_ld_wait4(a4.x, a4.y, a4.z, a4.w);
+                    const float2 a0 = pk_add(cmk(a4.x, a4.y), pk), a1 = pk_add(cmk(a4.z, a4.w), pm);
+                    tm_st4(tacc + 4 * pp, a0.x, a0.y, a1.x, a1.y);
+                } else
+#endif
+                {
+                    a4 = sacc[pp * G];
                     const float2 a0 = pk_add(cmk(a4.x, a4.y), pk), a1 = pk_add(cmk(a4.z, a4.w), pm);
                     sacc[pp * G] = make_float4(a0.x, a0.y, a1.x, a1.y);
                 }
@@ -233,13 +303,40 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
                     if (actA) rowA[M / 2] = pw.x;
                     if (actB) rowA[M / 2 + KOUT] = pw.y;
                 }
-                float2* const q = reinterpret_cast<float2*>(sacc + 8 * G);
-                *q = pk_add(*q, pw);
+#ifndef B2S_EMU
+                if constexpr (ACC_TMEM) {
+                    float2 am;
+                    tm_ld2(tacc + 32, am.x, am.y);
+                    tm_ld_wait2(am.x, am.y);
+                    am = pk_add(am, pw);
+                    tm_st2(tacc + 32, am.x, am.y);
+                } else
+#endif
+                if (is0) {
+                    float2* const q = reinterpret_cast<float2*>(sacc + 8 * G);
+                    *q = pk_add(*q, pw);
+                }
             }
             rowA += p.out_batch_stride;
         }
 
         // ---- the block's partial sums: p.acc[blk][frame][bin] ----
+#ifndef B2S_EMU
+        if constexpr (ACC_TMEM) {        // through shared memory, so that the write-out below is the same code
+            tm_st_wait();
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                float4 a4;
+                tm_ld4(tacc + 4 * pp, a4.x, a4.y, a4.z, a4.w);
+                tm_ld_wait4(a4.x, a4.y, a4.z, a4.w);
+                sacc[pp * G] = a4;
+            }
+            float2 am;
+            tm_ld2(tacc + 32, am.x, am.y);
+            tm_ld_wait2(am.x, am.y);
+            *reinterpret_cast<float2*>(sacc + 8 * G) = am;
+        }
+#endif
         if (uvalid) {
             float* const sA = p.acc + ((long long)blk * p.nframes + f) * KOUT;
 #pragma unroll
@@ -259,6 +356,15 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
             }
         }
     }
+#ifndef B2S_EMU
+    if constexpr (ACC_TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" : : : "memory");
+        __syncthreads();
+        if (tid < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                         : : "r"(tacc & 0xffffu), "n"(DuoSumPlan::TMEM_COLS) : "memory");
+    }
+#endif
     if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
         __syncthreads();
         if (tid == 0) {

@@ -68,8 +68,9 @@ struct CudaLauncher {
 };
 
 
-// the sum-fused frame-duo kernel for hop = slots * 32 (b2s_inst_sum.cu); nullptr if there is none
-const void* duo_sum_kernel_for(int x_is_f64, int slots);
+// the sum-fused frame-duo kernel for hop = slots * 32 (b2s_inst_sum.cu); nullptr if there is none.
+// acc_tmem: running sums in tensor memory (else shared memory)
+const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
 
 // dispatch_tg<Tin, MODE> instantiated in b2s_inst_*.cu
 int dispatch_f32_plain(const StftArgs& a, CudaLauncher& L);
