@@ -46,10 +46,11 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(fused=True):
     """Per-launch DRAM bytes of the STFT kernel from the committed ncu --set full capture."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["stft_psd_c2_bytes_per_launch"]
+        key = "stft_psd_sum_c2_bytes_per_launch" if fused else "stft_psd_c2_bytes_per_launch"
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
     except Exception:
         return None
 
@@ -332,7 +333,7 @@ def run_gpu(args):
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
                                       f"({collective}, in stream order after the cross-sweep sum, inside the timed region)"},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(fused),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
                          "kernel_ms": kern_ms, "frac_of_nominal_8000": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.nbytes),
