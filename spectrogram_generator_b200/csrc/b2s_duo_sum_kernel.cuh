@@ -6,12 +6,14 @@
 // kernel that reads every per-sweep spectrogram back (318 MB for C2: 30 % of the step).  Here a
 // lane group keeps ONE frame duo (f, f + 1) and walks over a block of consecutive sweeps: each
 // per-sweep row is stored exactly as before (bit-identical: the per-frame arithmetic is the
-// same), and the 2 x 257 power values are also added, in sweep order, into accumulators that
-// never leave the registers (17 packed values per lane).  A unit ends by writing its block's
-// partial sums; a fold over the sweep blocks (batch_sum_kernel, a few MB) finishes the sum.  The
-// order of the additions is fixed (sweep order inside a block, block order in the fold):
-// deterministic.  The price is the sliding register window -- every duo loads its 16 + S slots
-// afresh, one sweep ahead -- against reading the whole output a second time.
+// same), and the 2 x 257 power values are also added, in sweep order, into running sums that
+// never leave the SM: 34 values per lane, kept in tensor memory (ACC_TMEM = 1, the product
+// path) or in shared memory (the CPU emulator's path and the twin the launch takes its
+// residency from).  A unit ends by writing its block's partial sums; a fold over the sweep
+// blocks (batch_sum_kernel, a few MB) finishes the sum.  The order of the additions is fixed
+// (sweep order inside a block, block order in the fold): deterministic.  The price is the
+// sliding register window -- every duo loads its 16 + S slots afresh, one sweep ahead --
+// against reading the whole output a second time.
 #pragma once
 
 #include "b2s_duo_kernel.cuh"
@@ -69,7 +71,9 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
     const int tid = (int)threadIdx.x;
     const int grp = tid / G;
     const int t = tid & (G - 1);
-    float4* const buf = sm4 + DP::TAB + grp * DP::BUF;
+    // exchange buffer of the duo: a plane of real and a plane of imaginary parts, [16][ROW] float2 (A, B) each
+    float2* const xre = reinterpret_cast<float2*>(sm4 + DP::TAB + grp * DP::BUF);
+    float2* const xim = xre + 16 * ROW;
     // the block sums of the duo: [slot][lane] float4 = (bin k: A, B; bin 256 - k: A, B), slot 8 = bin 128
     float4* const sacc = sm4 + DP::TAB + DP::FPC * DP::BUF + grp * DuoSumPlan::ACC + t;
 
@@ -222,15 +226,16 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const cpx2 z = v[perm16(q)];
-                buf[ROW * t + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
+                xre[ROW * t + q] = z.re;           // two conflict-free 64-bit stores straight from the register
+                xim[ROW * t + q] = z.im;           // pairs: a 128-bit store first gathers them with 4 MOVs.
+                                                   // (1-2 % here; the per-sweep kernel loses 4 % with it)
             }
             __syncwarp();
 
             // ---- pass 1: lane q = t; twiddle W_256^(t' q), radix-16 over t' -> Z[q + 16 p] ----
 #pragma unroll
             for (int tt = 0; tt < 16; ++tt) {
-                const float4 q4 = buf[ROW * tt + t];
-                v[tt] = cpx2{cmk(q4.x, q4.y), cmk(q4.z, q4.w)};
+                v[tt] = cpx2{xre[ROW * tt + t], xim[ROW * tt + t]};
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {

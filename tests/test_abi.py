@@ -63,3 +63,26 @@ def test_bad_arguments_are_reported_before_any_device_work():
         _lib.check(call(kmin=5, kmax=4), "b2s_stft_psd_f32")
     with pytest.raises(NotImplementedError):
         _lib.check(call(nperseg=40000), "b2s_stft_psd_f32")
+
+
+def test_sum_call_reports_bad_arguments_before_any_device_work():
+    """b2s_stft_psd_sum_f32: same validation as b2s_stft_psd_f32, plus its own buffers."""
+    lib = _lib.load()
+    x = np.zeros(2 * 1024, np.float32)
+    w = np.ones(512, np.float32)
+    o = np.zeros(2 * 5 * 257, np.float32)
+    s = np.zeros(5 * 257, np.float32)
+    scr = np.zeros(2 * 5 * 257, np.float32)
+
+    def call(**kw):
+        a = dict(x=x.ctypes.data, batch=2, n=1024, xs=1024, nperseg=512, hop=128, w=w.ctypes.data, det=1,
+                 scale=1.0, f0=0, nf=5, out=o.ctypes.data, os=5 * 257, s=s.ctypes.data, ps=0.5, scr=scr.ctypes.data)
+        a.update(kw)
+        return lib.b2s_stft_psd_sum_f32(a["x"], a["batch"], a["n"], a["xs"], a["nperseg"], a["hop"], a["w"], a["det"],
+                                        a["scale"], a["f0"], a["nf"], a["out"], a["os"], a["s"], a["ps"], a["scr"], None)
+    assert call(hop=0) == _lib.B2S_ERR_BAD_ARG
+    assert call(nf=6) == _lib.B2S_ERR_BAD_ARG and b"frame range" in lib.b2s_last_error()
+    assert call(s=None) == _lib.B2S_ERR_BAD_ARG and b"sum_out" in lib.b2s_last_error()
+    assert call(scr=None) == _lib.B2S_ERR_BAD_ARG
+    assert call(x=None) == _lib.B2S_ERR_BAD_ARG
+    assert call(nperseg=40000) == _lib.B2S_ERR_UNSUPPORTED
