@@ -398,7 +398,9 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
         row_bytes = F * kout * 4
         # work items: (b0, b1, f0, f1)
         items = []
-        if B * row_bytes <= _PIPE_CHUNK_BYTES or not per_sweep:
+        # with a sum the chunking depends on the sizes only, so that the order of its additions --
+        # and with it every bit of the mean -- does not depend on whether the rows are copied back
+        if B * row_bytes <= _PIPE_CHUNK_BYTES or not (per_sweep or want_sum):
             items.append((0, B, 0, F))
         elif B >= 4:
             step = max(1, _PIPE_CHUNK_BYTES // row_bytes)
@@ -426,14 +428,20 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
             return S, total
         s_in.wait_stream(cur)
         s_out.wait_stream(cur)
-        for (b0, b1, f0, f1) in items:
+        # chunks of whole sweeps: rows and the chunk's sum in one pass, the chunk sums folded at the end
+        fused_sum = (want_sum and kout == plan.nbins and out_mode == 0
+                     and all(f0 == 0 and f1 == F for (_, _, f0, f1) in items))
+        parts = torch.empty((len(items), F, kout), dtype=torch.float32, device=dev) if fused_sum else None
+        for i, (b0, b1, f0, f1) in enumerate(items):
             lo, hi = (0, n) if (f0 == 0 and f1 == F) else (f0 * plan.hop, (f1 - 1) * plan.hop + plan.nperseg)
             with torch.cuda.stream(s_in):
                 x_d[b0:b1, lo:hi].copy_(h_in[b0:b1, lo:hi], non_blocking=pinned)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
             cur.wait_event(ev_in)
-            if f0 == 0 and f1 == F:
+            if fused_sum:
+                eng.stft_psd_sum(x_d[b0:b1], plan, out=S_d[b0:b1], sum_out=parts[i])
+            elif f0 == 0 and f1 == F:
                 eng.stft_psd(x_d[b0:b1], plan, out=S_d[b0:b1], kmin=kmin, kmax=kmax, out_mode=out_mode,
                              db_floor=db_floor)
             else:
@@ -445,7 +453,10 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_k)
                     h_out[b0:b1, f0:f1].copy_(S_d[b0:b1, f0:f1], non_blocking=True)
-        total = eng.batch_sum(S_d, sum_scale) if want_sum else None
+        if fused_sum:
+            total = eng.batch_sum(parts, sum_scale)
+        else:
+            total = eng.batch_sum(S_d, sum_scale) if want_sum else None
         if per_sweep:
             s_out.synchronize()
         cur.synchronize()             # x_d / S_d were used on side streams: keep them alive until here
