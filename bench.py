@@ -186,9 +186,14 @@ def run_gpu(args):
     # The all-reduce of the partial mean is issued in stream order after the cross-sweep sum.
     # Diagnostics (measured on 2 GPUs, 200 steps: none 0.222 ms/step, sync 0.237, async 1.23 -- async
     # NCCL kernels spin beside the persistent STFT grids of their peers; reserving SMs for them with
-    # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = peer (default) | sync | async | none.
-    mode = os.environ.get("B2S_BENCH_ALLREDUCE", "peer")
-    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "0")))
+    # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = overlap (default) | peer | sync | async | none.
+    # "overlap": the peer kernel on a high-priority side stream, so the all-reduce of step i runs beside the
+    # STFT of step i + 1, in the CTA slots of 5 SMs the STFT grid leaves free (b2s_set_reserved_sms).
+    mode = os.environ.get("B2S_BENCH_ALLREDUCE", "overlap")
+    overlap = (mode == "overlap")
+    if overlap:
+        mode = "peer"
+    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "5" if (overlap and world > 1) else "0")))
     from spectrogram_generator_b200 import _lib
     _lib.load().b2s_set_reserved_sms(reserve)
 
@@ -205,12 +210,13 @@ def run_gpu(args):
     if world > 1 and mode == "peer":
         try:
             from spectrogram_generator_b200.distributed import PeerMeanReducer
-            peer = PeerMeanReducer(plan.nframes * plan.nbins, dev)
+            peer = PeerMeanReducer(plan.nframes * plan.nbins, dev, overlap=overlap)
         except Exception as e:          # pragma: no cover
             if rank == 0:
                 print(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             mode = "sync"
-    collective = {"peer": "b2s_peer_allreduce_f32 (one kernel over NVLink peer memory)", "sync": "NCCL all_reduce",
+    collective = {"peer": "b2s_peer_allreduce_f32 (one kernel over NVLink peer memory" +
+                          ("; on a side stream, overlapping the next step's STFT)" if overlap else ")"), "sync": "NCCL all_reduce",
                   "async": "NCCL all_reduce (async)", "none": "none"}[mode] if world > 1 else "none"
 
     # per-sweep spectrograms + cross-sweep sum: ONE kernel keeps the running sums on chip while it
@@ -272,6 +278,8 @@ def run_gpu(args):
             mean = reduce_mean()
     for w, _ in pending:
         w.wait()
+    if peer is not None:
+        peer.wait()                  # overlap mode: the side stream's reduces join the timed stream
     end.record()
     sampler.sample()                 # all K steps are enqueued: this sample is taken under load
     torch.cuda.synchronize()
@@ -280,6 +288,14 @@ def run_gpu(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     elapsed_ms = start.elapsed_time(end)
+    # outside the timed region: the last step's mean against a plain recomputation (two-pass sum + NCCL)
+    check = None
+    if world > 1 and mode in ("peer", "sync"):
+        ref = eng.batch_sum(S, 1.0 / total_sweeps)
+        dist.all_reduce(ref)
+        err = float((mean.view(-1) - ref.view(-1)).abs().max() / ref.abs().max())
+        check = f"last step's mean vs batch_sum + NCCL all_reduce: max abs diff {err:.1e} of max"
+        assert err < 1e-5, check
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
     if world > 1:
         tt = torch.tensor([elapsed_ms, kern_ms], device=dev, dtype=torch.float64)
@@ -329,6 +345,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sweeps_per_gpu": B, "global_sweeps": total_sweeps,
                        "frames_per_sweep": F, "bins": K,
+                       "allreduce_check": check,
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
                                       f"({collective}, in stream order after the cross-sweep sum, inside the timed region)"},

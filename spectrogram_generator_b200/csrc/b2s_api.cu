@@ -444,7 +444,12 @@ int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned l
     if (rc != B2S_OK) return rc;
     const int block = 256;
     long long want = (elems + block - 1) / block;
-    const unsigned grid = (unsigned)(want < di.sm_count ? want : di.sm_count);     // all CTAs resident: they all wait
+    // every CTA waits for the peers, so never more CTAs than can be resident; with SMs reserved
+    // (b2s_set_reserved_sms: the all-reduce runs beside a persistent STFT grid of the next step) only
+    // as many as those SMs' CTA slots of the STFT kernels (3 per SM)
+    const int reserve = g_reserved_sms.load();
+    const long long cap = (reserve > 0 && reserve < di.sm_count) ? 3LL * reserve : di.sm_count;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     b2s::peer_allreduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out, post_scale,
                                                                          vec_ok);
     cudaError_t e = cudaGetLastError();

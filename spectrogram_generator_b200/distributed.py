@@ -158,12 +158,15 @@ class PeerMeanReducer:
     result is bit-identical on every rank.  For the [F, K] partial of config 2 (318 KB) this
     replaces ~30 us of collective latency per step by one ~10 us launch.
 
+    With ``overlap=True`` the reduce kernel runs on a high-priority side stream, so the all-reduce of
+    one step overlaps the kernels of the next (leave it CTA slots with ``b2s_set_reserved_sms``).
+
     Usage (every rank, same order):  ``r = PeerMeanReducer(F * K, device)``; per step
     ``engine().stft_psd_sum(x, plan, sum_out=r.partial())`` (or ``batch_sum(S, 1.0, out=r.partial())``)
     then ``mean = r.reduce(1.0 / total_sweeps)``.
     """
 
-    def __init__(self, elems: int, device, group=None):
+    def __init__(self, elems: int, device, group=None, overlap: bool = False):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -174,8 +177,14 @@ class PeerMeanReducer:
         self.elems = int(elems)
         self.device = torch.device(device)
         group = group if group is not None else dist.group.WORLD
-        self.stride = (self.elems + 3) // 4 * 4           # both halves 16-byte aligned: 128-bit peer loads
-        self.buf = symm_mem.empty(2 * self.stride, dtype=torch.float32, device=self.device)
+        # overlap: the all-reduce of step i runs on a side stream beside the kernels of step i + 1.
+        # A partial may then be overwritten only two reduces later, hence three buffers instead of two:
+        # slot e % 3 is rewritten for epoch e + 3 after this rank's reduce(e + 1) has completed, which
+        # it only does once every peer has announced e + 1, i.e. has finished reading epoch e.
+        self.overlap = bool(overlap)
+        self.nbuf = 3 if self.overlap else 2
+        self.stride = (self.elems + 3) // 4 * 4           # every slot 16-byte aligned: 128-bit peer loads
+        self.buf = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.world, self.rank = int(self.handle.world_size), int(self.handle.rank)
         if self.world > 16:
@@ -183,25 +192,57 @@ class PeerMeanReducer:
         self._bufs = [int(p) for p in self.handle.buffer_ptrs]
         self._pads = (ctypes.c_ulonglong * self.world)(*[int(p) for p in self.handle.signal_pad_ptrs])
         self.epoch = 0
+        self._done = {}                        # epoch -> event recorded after its reduce (overlap mode)
+        if self.overlap:
+            with torch.cuda.device(self.device):
+                self.side = torch.cuda.Stream(priority=-1)       # its few CTAs go first when slots free up
         self.handle.barrier()                  # pads and buffers exist on every rank before the first kernel
 
+    def _slot(self, epoch: int) -> int:
+        return epoch % self.nbuf
+
     def partial(self) -> torch.Tensor:
-        """Where this rank writes its partial of the coming ``reduce`` call."""
-        par = (self.epoch + 1) & 1
-        return self.buf[par * self.stride:par * self.stride + self.elems]
+        """Where this rank writes its partial of the coming ``reduce`` call.  In overlap mode the
+        current stream first waits until the slot's previous content has been read by every peer."""
+        nxt = self.epoch + 1
+        if self.overlap:
+            ev = self._done.pop(nxt - 2, None)
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+        k = self._slot(nxt)
+        return self.buf[k * self.stride:k * self.stride + self.elems]
 
     def reduce(self, post_scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Sum of all ranks' partials times ``post_scale`` -> ``out`` (allocated if None).  Enqueued
-        on the current stream; must be called by every rank, in the same order."""
+        """Sum of all ranks' partials times ``post_scale`` -> ``out`` (allocated if None).  Must be
+        called by every rank, in the same order.  Enqueued on the current stream -- in overlap mode on
+        the reducer's side stream, after what the current stream has done so far; ``wait()`` (or the
+        next-but-one ``partial()``) joins it."""
         self.epoch += 1
-        par = self.epoch & 1
+        k = self._slot(self.epoch)
         if out is None:
             out = torch.empty(self.elems, dtype=torch.float32, device=self.device)
-        bufs = (self._ct.c_ulonglong * self.world)(*[b + 4 * par * self.stride for b in self._bufs])
-        with torch.cuda.device(self.device):
-            rc = self._lib.b2s_peer_allreduce_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
-                                                  out.data_ptr(), float(post_scale),
-                                                  torch.cuda.current_stream().cuda_stream)
+        bufs = (self._ct.c_ulonglong * self.world)(*[b + 4 * k * self.stride for b in self._bufs])
         from . import _lib
-        _lib.check(rc, "b2s_peer_allreduce_f32")
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            if self.overlap:
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                self.side.wait_event(ready)
+                stream = self.side
+            else:
+                stream = cur
+            rc = self._lib.b2s_peer_allreduce_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
+                                                  out.data_ptr(), float(post_scale), stream.cuda_stream)
+            _lib.check(rc, "b2s_peer_allreduce_f32")
+            if self.overlap:
+                out.record_stream(self.side)
+                done = torch.cuda.Event()
+                done.record(self.side)
+                self._done[self.epoch] = done
         return out
+
+    def wait(self):
+        """Overlap mode: make the current stream wait for every reduce issued so far."""
+        if self.overlap:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)

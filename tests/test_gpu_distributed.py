@@ -64,6 +64,20 @@ def _worker(rank, world, port, out_dir):
             both = [torch.empty_like(got) for _ in range(world)]
             dist.all_gather(both, got)
             assert all(torch.equal(both[0], b) for b in both), "peer all-reduce differs between ranks"
+        # overlap mode: the reduces run on a side stream (three buffers), results as NCCL's
+        red3 = D.PeerMeanReducer(elems, dev, overlap=True)
+        outs, refs = [], []
+        for it in range(7):
+            part = torch.rand(elems, generator=g).to(dev) * (it + 1)
+            red3.partial().copy_(part)
+            outs.append(red3.reduce(0.5))
+            ref = part.clone()
+            dist.all_reduce(ref)
+            refs.append(ref * 0.5)
+        red3.wait()
+        torch.cuda.synchronize()
+        for o, r in zip(outs, refs):
+            torch.testing.assert_close(o, r, rtol=1e-6, atol=0)
         # ... and the same reducer behind the sharded mean
         red2 = D.PeerMeanReducer(309 * 257, dev)
         _, _, mean_p = D.mean_spectrogram_sharded(x[lo:hi], 37, fs=fs, reducer=red2, **kw)

@@ -128,6 +128,11 @@ def test_fused_sum_matches_the_two_pass_sum_and_the_public_mean(monkeypatch):
     eng = sg.engine()
     xd = torch.from_numpy(x).cuda()
     S, tot = eng.stft_psd_sum(xd, plan)
+    # running sums in shared memory instead of tensor memory: the same additions in the same order
+    monkeypatch.setenv("B2S_SUM_ACC_SMEM", "1")
+    S1, tot1 = eng.stft_psd_sum(xd, plan)
+    monkeypatch.delenv("B2S_SUM_ACC_SMEM")
+    assert torch.equal(S1, S) and torch.equal(tot1, tot)
     monkeypatch.setenv("B2S_NO_FUSED_SUM", "1")
     S0, tot0 = eng.stft_psd_sum(xd, plan)
     monkeypatch.delenv("B2S_NO_FUSED_SUM")
