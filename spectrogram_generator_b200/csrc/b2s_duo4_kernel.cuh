@@ -184,24 +184,42 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
             cpx2 v[16];
             if (p.detrend) {
                 // coarse per-frame means (pivots): per-slot sums in a fixed frame-relative order
-                constexpr int NB = 16 / S;
-                float blk[NB + 1];
-#pragma unroll
-                for (int bi = 0; bi <= NB; ++bi) {
-                    float ss[S];
-#pragma unroll
-                    for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
-#pragma unroll
-                    for (int w = S / 2; w >= 1; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
-                    blk[bi] = ss[0];
-                }
                 float2 cs;
-                if constexpr (NB == 2) cs = cmk(blk[0] + blk[1], blk[1] + blk[2]);
-                else if constexpr (NB == 4) cs = cmk((blk[0] + blk[1]) + (blk[2] + blk[3]), (blk[1] + blk[2]) + (blk[3] + blk[4]));
-                else cs = cmk(((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7])),
-                              ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8])));
+                if constexpr (S >= 14) {
+                    // frames A and B share (almost) nothing: the same fixed tree over each frame's own 16 slots
+                    float sa[16], sb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        sa[i] = cur[i].x + cur[i].y;
+                        sb[i] = cur[i + S].x + cur[i + S].y;
+                    }
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; ++i) {
+                            sa[i] += sa[i + w];
+                            sb[i] += sb[i + w];
+                        }
+                    cs = cmk(sa[0], sb[0]);
+                } else {
+                    constexpr int NB = 16 / S;
+                    float blk[NB + 1];
+#pragma unroll
+                    for (int bi = 0; bi <= NB; ++bi) {
+                        float ss[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
+#pragma unroll
+                        for (int w = S / 2; w >= 1; w >>= 1)
+#pragma unroll
+                            for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
+                        blk[bi] = ss[0];
+                    }
+                    if constexpr (NB == 2) cs = cmk(blk[0] + blk[1], blk[1] + blk[2]);
+                    else if constexpr (NB == 4) cs = cmk((blk[0] + blk[1]) + (blk[2] + blk[3]), (blk[1] + blk[2]) + (blk[3] + blk[4]));
+                    else cs = cmk(((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7])),
+                                  ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8])));
+                }
                 const float2 cm = pk_muls(duo4_group_sum<LOG2N>(cs, grp, j, red), 1.0f / (float)N);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {

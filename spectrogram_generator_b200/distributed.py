@@ -87,6 +87,7 @@ def mean_spectrogram_sharded(x_local, total_sweeps: int, fs=1.0, window=("tukey"
                                    sum_out=reducer.partial() if use_peer else None)
         if use_peer:
             mean = reducer.reduce(1.0 / float(total_sweeps)).view(S.shape[1:])
+            reducer.wait()                       # overlap mode: the result is used on this stream right away
         else:
             if ws > 1:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)

@@ -16,6 +16,11 @@ namespace emu { Cta* g_cta = nullptr; }
 
 using namespace b2s;
 
+// which kernel family the last emu_stft_psd call ran (tests assert that a shape reaches the kernel it is meant for)
+static int g_last_family = 0;
+extern "C" int emu_last_family() { return g_last_family; }
+enum { FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
+
 struct EmuLauncher {
     StftParams p;
     unsigned grid;
@@ -27,6 +32,7 @@ struct EmuLauncher {
     int work[2] = {0, 0};
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs&) {
+        g_last_family = FAM_DUO256;
         using DP = Duo256Plan;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -35,6 +41,7 @@ struct EmuLauncher {
     }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const StftArgs&) {
+        g_last_family = FAM_DUO4;
         using DP = Duo4Plan<LOG2N>;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -43,6 +50,7 @@ struct EmuLauncher {
     }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs&) {
+        g_last_family = FAM_DUO_CTA;
         using DP = DuoCtaPlan<LOG2N>;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -51,6 +59,7 @@ struct EmuLauncher {
     }
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs&) {
+        g_last_family = FAM_DUO;
         using DP = DuoPlan;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -59,6 +68,7 @@ struct EmuLauncher {
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs&) {
+        g_last_family = FAM_WARP;
         using WP = WarpPlan<LOG2N>;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -67,6 +77,7 @@ struct EmuLauncher {
     }
     template <int LOG2N, typename Tin, int MODE>
     int big(const StftArgs&) {
+        g_last_family = FAM_BIG;
         using BP = BigPlan<LOG2N>;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -75,6 +86,7 @@ struct EmuLauncher {
     }
     template <int LOG2N, typename Tin, int MODE>
     int cta(const StftArgs&) {
+        g_last_family = FAM_CTA;
         using PL = Plan<LOG2N>;
         StftParams q = p;
         if (dynamic_units) q.work = work;
@@ -93,6 +105,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     std::string err;
     if (validate_args(a, err) < 0) return validate_args(a, err);
     if (nperseg_support(nperseg) == 2) {
+        g_last_family = FAM_DFT;
         DftParams dp{};
         fill_dft_params(a, dp);
         std::vector<float> tw;

@@ -199,7 +199,7 @@ def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):
     kernels: odd and even frame counts, runs cut at odd lengths, crop / frame range / band power,
     float64 samples, against the oracle; the result of a frame must not depend on the chunking."""
     nfr = 6 + nframes_extra
-    n = nperseg + hop * (nfr - 1) + 5
+    n = nperseg + hop * (nfr - 1) + 6          # even rows: the packed kernels need 8-byte aligned frames
     x = signal(3, n, nperseg + hop + nframes_extra, dc=-3.0 if detrend else 0.0)
     kw = dict(window="hann", nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
     plan = plan_for(n, 5000.0, **kw)
@@ -207,6 +207,7 @@ def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):
     _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=5000.0, **kw)
     So = np.moveaxis(So, -1, -2)
     a = emu.stft_psd(x, plan, chunk=3, grid=1)           # odd run length: last duo of a run is half empty
+    assert emu.last_family() == ("duo" if nperseg == 512 else "duo256")
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"duo {nperseg}/{hop}")
     assert np.array_equal(a, b)
@@ -274,6 +275,7 @@ def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):
     _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
     So = np.moveaxis(So, -1, -2)
     a = emu.stft_psd(x, plan, chunk=3, grid=1)
+    assert emu.last_family() == "duo_cta"       # odd rows / hops outside the four-step kernel's set
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"duo cta {nperseg}/{hop}")
     assert np.array_equal(a, b)
@@ -284,15 +286,15 @@ def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
 
 
-@pytest.mark.parametrize("nperseg,hop", [(1024, 256), (1024, 128), (1024, 512), (2048, 512), (2048, 1024),
-                                         (4096, 1024), (4096, 512)])
+@pytest.mark.parametrize("nperseg,hop", [(1024, 256), (1024, 128), (1024, 512), (1024, 896), (1024, 1024),
+                                         (2048, 512), (2048, 1024), (4096, 1024), (4096, 512)])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_four_step_duo_kernel(emu, nperseg, hop, detrend):
     """nperseg 1024 / 2048 / 4096 with hop = S * nperseg/16 run on the four-step duo kernel
     (256-point sub-transforms per half-warp + fused radix-R final stage): odd frame counts, runs
     cut at odd lengths, crop / frame range / band power, float64 samples; chunking-invariant."""
     nfr = 5
-    n = nperseg + hop * (nfr - 1) + 3
+    n = nperseg + hop * (nfr - 1) + 4          # even rows: the packed kernels need 8-byte aligned frames
     x = signal(2, n, nperseg + hop + 1, dc=-3.0 if detrend else 0.0)
     kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
     plan = plan_for(n, 48000.0, **kw)
@@ -300,6 +302,7 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend):
     _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
     So = np.moveaxis(So, -1, -2)
     a = emu.stft_psd(x, plan, chunk=3, grid=1)
+    assert emu.last_family() == "duo4"
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"duo4 {nperseg}/{hop}")
     assert np.array_equal(a, b)

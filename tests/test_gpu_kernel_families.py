@@ -17,6 +17,7 @@ CASES = [
     (512, 128), (512, 64), (512, 256),                    # frame-duo kernel
     (256, 64), (256, 32), (256, 128),                     # frame-duo kernel, 8 lanes
     (1024, 256), (1024, 128), (1024, 512),                # four-step duo, R = 2
+    (1024, 1024),                                         # four-step duo without overlap (1024/896 below: odd rows permitting)
     (2048, 512), (2048, 1024), (4096, 1024), (4096, 512), # four-step duo, R = 4 / 8
     (1024, 896), (2048, 333), (4096, 3584),               # duo CTA kernel (reference default overlap, odd hop)
     (512, 448), (256, 37), (128, 32), (64, 16),           # warp kernel

@@ -111,6 +111,13 @@ class Emulator:
         assert rc == 0, rc
         return out
 
+    FAMILIES = {1: "duo256", 2: "duo4", 3: "duo_cta", 4: "duo", 5: "warp", 6: "big", 7: "cta", 8: "dft"}
+
+    def last_family(self):
+        """Kernel family the last stft_psd / band_power call ran."""
+        self.lib.emu_last_family.restype = ctypes.c_int
+        return self.FAMILIES.get(self.lib.emu_last_family())
+
     def stft_psd_sum(self, x2d, plan, post_scale=1.0, grid=2, max_blocks=64):
         """The sum-fused frame-duo kernel + fold: (rows[B, F, K], sum[F, K], blocks used)."""
         x2d = np.ascontiguousarray(x2d)

@@ -108,6 +108,8 @@ int main_cta(int B, int N, int HOP) {
     if (HOP * 16 == NP * 4) run("duo4<LOG2N,float,4,0>", stft_psd_duo4_kernel<LOG2N, float, 4, 0>, D4::NT, D4::SMEM, D4::FPC, c);
     if (HOP * 16 == NP * 2) run("duo4<LOG2N,float,2,0>", stft_psd_duo4_kernel<LOG2N, float, 2, 0>, D4::NT, D4::SMEM, D4::FPC, c);
     if (HOP * 16 == NP * 8) run("duo4<LOG2N,float,8,0>", stft_psd_duo4_kernel<LOG2N, float, 8, 0>, D4::NT, D4::SMEM, D4::FPC, c);
+    if (HOP * 16 == NP * 14) run("duo4<LOG2N,float,14,0>", stft_psd_duo4_kernel<LOG2N, float, 14, 0>, D4::NT, D4::SMEM, D4::FPC, c);
+    if (HOP * 16 == NP * 16) run("duo4<LOG2N,float,16,0>", stft_psd_duo4_kernel<LOG2N, float, 16, 0>, D4::NT, D4::SMEM, D4::FPC, c);
     return 0;
 }
 
