@@ -304,7 +304,8 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     const long long elems = nframes * (nperseg / 2 + 1);
     const char* off = getenv("B2S_NO_FUSED_SUM");
     const char* noduo = getenv("B2S_NO_DUO");
-    const int slots = ((off && atoi(off)) || (noduo && atoi(noduo)) || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
+    int slots = ((off && atoi(off)) || (noduo && atoi(noduo)) || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
+    if (slots > 8) slots = 0;           // hop 448 / 512: per-sweep frame-duo kernel, no sum-fused variant
     if (slots) return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
     // every other shape: the per-sweep kernel of its family, then the two-pass sum
     int rc = stft_entry<Tin>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR, 0.f, 0,

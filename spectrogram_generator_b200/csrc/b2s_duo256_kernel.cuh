@@ -1,4 +1,4 @@
-// Frame-duo STFT -> PSD kernel, nperseg = 256, hop = S * 16 samples (S = 2, 4, 8): the scheme of
+// Frame-duo STFT -> PSD kernel, nperseg = 256, hop = S * 16 samples (S = 2, 4, 8, 14, 16): the scheme of
 // b2s_duo_kernel.cuh (two consecutive frames packed in fp32x2 registers, sliding register
 // window, one shared-memory transpose, shuffle mirror exchange) for M = 128 = 16 x 8:
 //   * 8 lanes own a duo (4 duos per warp), 16 complex points per frame per lane;
@@ -123,24 +123,42 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
             // ---- detrend + window, packing frame A (slots 0..15) and B (slots S..S+15) ----
             cpx2 v[16];
             if (p.detrend) {
-                constexpr int NB = 16 / S;
-                float blk[NB + 1];
-#pragma unroll
-                for (int bi = 0; bi <= NB; ++bi) {
-                    float ss[S];
-#pragma unroll
-                    for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
-#pragma unroll
-                    for (int w = S / 2; w >= 1; w >>= 1)
-#pragma unroll
-                        for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
-                    blk[bi] = ss[0];
-                }
                 float2 cs;
-                if constexpr (NB == 2) cs = cmk(blk[0] + blk[1], blk[1] + blk[2]);
-                else if constexpr (NB == 4) cs = cmk((blk[0] + blk[1]) + (blk[2] + blk[3]), (blk[1] + blk[2]) + (blk[3] + blk[4]));
-                else cs = cmk(((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7])),
-                              ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8])));
+                if constexpr (S >= 14) {
+                    // frames A and B share (almost) nothing: the same fixed tree over each frame's own 16 slots
+                    float sa[16], sb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        sa[i] = cur[i].x + cur[i].y;
+                        sb[i] = cur[i + S].x + cur[i + S].y;
+                    }
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; ++i) {
+                            sa[i] += sa[i + w];
+                            sb[i] += sb[i + w];
+                        }
+                    cs = cmk(sa[0], sb[0]);
+                } else {
+                    constexpr int NB = 16 / S;
+                    float blk[NB + 1];
+#pragma unroll
+                    for (int bi = 0; bi <= NB; ++bi) {
+                        float ss[S];
+#pragma unroll
+                        for (int i = 0; i < S; ++i) ss[i] = cur[bi * S + i].x + cur[bi * S + i].y;
+#pragma unroll
+                        for (int w = S / 2; w >= 1; w >>= 1)
+#pragma unroll
+                            for (int i = 0; i < w; ++i) ss[i] += ss[i + w];
+                        blk[bi] = ss[0];
+                    }
+                    if constexpr (NB == 2) cs = cmk(blk[0] + blk[1], blk[1] + blk[2]);
+                    else if constexpr (NB == 4) cs = cmk((blk[0] + blk[1]) + (blk[2] + blk[3]), (blk[1] + blk[2]) + (blk[3] + blk[4]));
+                    else cs = cmk(((blk[0] + blk[1]) + (blk[2] + blk[3])) + ((blk[4] + blk[5]) + (blk[6] + blk[7])),
+                                  ((blk[1] + blk[2]) + (blk[3] + blk[4])) + ((blk[5] + blk[6]) + (blk[7] + blk[8])));
+                }
 #pragma unroll
                 for (int o = G / 2; o >= 1; o >>= 1)
                     cs = pk_add(cs, cmk(__shfl_xor_sync(0xffffffffu, cs.x, o), __shfl_xor_sync(0xffffffffu, cs.y, o)));

@@ -110,7 +110,33 @@ struct DuoPlan {
 // fixed frame-relative order: blocks of S slots first (frames A and B share 16/S - 1 blocks).
 template <int S>
 B2S_DEVICE void duo_coarse_means(const float2 (&cur)[16 + S], float& cA, float& cB) {
-    constexpr int NB = 16 / S;
+    if constexpr (S >= 14) {
+        // frames A and B share (almost) nothing: the same fixed tree over each frame's own 16 slots
+        float sa[16], sb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            sa[i] = cur[i].x + cur[i].y;
+            sb[i] = cur[i + S].x + cur[i + S].y;
+        }
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) {
+                sa[i] += sa[i + w];
+                sb[i] += sb[i + w];
+            }
+        cA = sa[0];
+        cB = sb[0];
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            cA += __shfl_xor_sync(0xffffffffu, cA, o);
+            cB += __shfl_xor_sync(0xffffffffu, cB, o);
+        }
+        cA *= 1.0f / 512.0f;
+        cB *= 1.0f / 512.0f;
+        return;
+    }
+    constexpr int NB = (S >= 14) ? 1 : 16 / S;
     float blk[NB + 1];
 #pragma unroll
     for (int bi = 0; bi <= NB; ++bi) {

@@ -167,7 +167,7 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
     std::string err;
     if (validate_args(a, err) < 0) return validate_args(a, err);
     const int slots = duo_slots(a, ilog2_exact(nperseg));
-    if (!slots) return -200;
+    if (!slots || slots > 8) return -200;
     StftParams p{};
     const int blocks = plan_stft_sum(a, (long long)grid * DuoPlan::FPC, max_blocks, p, err);
     if (blocks < 0) return blocks;

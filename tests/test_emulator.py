@@ -191,7 +191,8 @@ def test_fused_band_power(emu, nperseg):
     np.testing.assert_allclose(band, So[:, kmin:kmax + 1, :].sum(axis=1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("nperseg,hop", [(512, 64), (512, 128), (512, 256), (256, 32), (256, 64), (256, 128)])
+@pytest.mark.parametrize("nperseg,hop", [(512, 64), (512, 128), (512, 256), (512, 448), (512, 512),
+                                         (256, 32), (256, 64), (256, 128), (256, 224), (256, 256)])
 @pytest.mark.parametrize("nframes_extra", [0, 1])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):

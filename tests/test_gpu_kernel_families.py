@@ -14,13 +14,13 @@ pytestmark = pytest.mark.gpu
 
 # (nperseg, hop) -> family that runs it
 CASES = [
-    (512, 128), (512, 64), (512, 256),                    # frame-duo kernel
-    (256, 64), (256, 32), (256, 128),                     # frame-duo kernel, 8 lanes
+    (512, 128), (512, 64), (512, 256), (512, 512),        # frame-duo kernel ((512, 448) below: even rows permitting)
+    (256, 64), (256, 32), (256, 128), (256, 224), (256, 256),   # frame-duo kernel, 8 lanes (224: even rows permitting)
     (1024, 256), (1024, 128), (1024, 512),                # four-step duo, R = 2
     (1024, 1024),                                         # four-step duo without overlap (1024/896 below: odd rows permitting)
     (2048, 512), (2048, 1024), (4096, 1024), (4096, 512), # four-step duo, R = 4 / 8
     (1024, 896), (2048, 333), (4096, 3584),               # duo CTA kernel (reference default overlap, odd hop)
-    (512, 448), (256, 37), (128, 32), (64, 16),           # warp kernel
+    (512, 448), (256, 37), (128, 32), (64, 16),           # frame-duo (512/448, even rows) / warp kernel
     (8192, 2048), (16384, 4096),                          # three-pass CTA kernel
     (1000, 875), (600, 150),                              # direct DFT
 ]
@@ -93,7 +93,7 @@ def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg,
     (512, 128, 37, 10, 0), (512, 64, 5, 7, 0), (512, 256, 130, 6, 0), (512, 128, 2, 1, 0),
     (512, 128, 9, 8, 1),            # odd row length: rows only 4-byte aligned -> two-pass path inside the library
     (512, 128, 1, 12, 0),           # one sweep
-    (1024, 256, 40, 9, 0), (256, 64, 300, 11, 0), (600, 150, 7, 5, 0),       # no fused kernel for these shapes
+    (1024, 256, 40, 9, 0), (256, 64, 300, 11, 0), (600, 150, 7, 5, 0), (512, 448, 20, 6, 0),   # no fused kernel for these shapes
 ])
 def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
     """Engine.stft_psd_sum (b2s_stft_psd_sum_f32/_f64): the rows are bit-identical to stft_psd's,

@@ -63,6 +63,11 @@ def main():
         shapes += [(16, 5_760_000, 4096, 1024)]
     if args.set == "n1024":
         shapes += [(1000, 40000, 1024, 256)]
+    if args.set == "refcall":       # the reference's own call form: Tukey(0.25), noverlap = nperseg // 8, and no overlap
+        for nperseg in (256, 512, 1024, 2048, 4096, 8192):
+            shapes.append((1000, 200_000, nperseg, nperseg - nperseg // 8, ("tukey", .25)))
+        for nperseg in (256, 512, 1024):
+            shapes.append((1000, 200_000 // nperseg * nperseg, nperseg, nperseg, "hann"))
     if args.set == "n1024ref":      # nperseg 1024 at the reference's default overlap and without overlap
         shapes += [(1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 1024, 896),
                    (1000, 40960, 1024, 1024)]
@@ -71,7 +76,8 @@ def main():
             for ov in (0.5, 0.75, 0.875):
                 shapes.append((1024, 100_000, nperseg, int(nperseg * (1 - ov))))
     for s in shapes:
-        print(json.dumps(time_shape(*s, flush=flush)), flush=True)
+        kw = {"window": s[4]} if len(s) > 4 else {}
+        print(json.dumps(time_shape(*s[:4], flush=flush, **kw)), flush=True)
 
 
 if __name__ == "__main__":

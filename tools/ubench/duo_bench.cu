@@ -140,6 +140,12 @@ int main_256(int B, int N, int HOP) {
     if (HOP == 64) {
         run("warp<8,float,4,0>", stft_psd_warp_kernel<8, float, 4, 0>, WP::NT, WP::SMEM, WP::FPC, c);
         run("duo256<float,4,0>", stft_psd_duo256_kernel<float, 4, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 224) {
+        run("warp<8,float,14,0>", stft_psd_warp_kernel<8, float, 14, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo256<float,14,0>", stft_psd_duo256_kernel<float, 14, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 256) {
+        run("warp<8,float,0,0>", stft_psd_warp_kernel<8, float, 0, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo256<float,16,0>", stft_psd_duo256_kernel<float, 16, 0>, DP::NT, DP::SMEM, DP::FPC, c);
     } else if (HOP == 32) {
         run("warp<8,float,2,0>", stft_psd_warp_kernel<8, float, 2, 0>, WP::NT, WP::SMEM, WP::FPC, c);
         run("duo256<float,2,0>", stft_psd_duo256_kernel<float, 2, 0>, DP::NT, DP::SMEM, DP::FPC, c);
@@ -159,7 +165,7 @@ int main(int argc, char** argv) {
         if (np == 4096) return main_cta<12>(b, n, hop);
         return 1;
     }
-    const int B = 1000, N = 40000, NP = 512, HOP = (argc > 1) ? atoi(argv[1]) : 128;
+    const int B = 1000, N = (argc > 2) ? atoi(argv[2]) : 40000, NP = 512, HOP = (argc > 1) ? atoi(argv[1]) : 128;
     const int F = (N - NP) / HOP + 1, K = NP / 2 + 1;
     Ctx c;
     cudaDeviceProp prop;
@@ -196,6 +202,12 @@ int main(int argc, char** argv) {
     } else if (HOP == 64) {
         run("warp<9,float,2,0>", stft_psd_warp_kernel<9, float, 2, 0>, WP::NT, WP::SMEM, WP::FPC, c);
         run("duo<float,2,0,MINB=3>", stft_psd_duo_kernel<float, 2, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 448) {
+        run("warp<9,float,14,0>", stft_psd_warp_kernel<9, float, 14, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo<float,14,0,MINB=3>", stft_psd_duo_kernel<float, 14, 0>, DP::NT, DP::SMEM, DP::FPC, c);
+    } else if (HOP == 512) {
+        run("warp<9,float,0,0>", stft_psd_warp_kernel<9, float, 0, 0>, WP::NT, WP::SMEM, WP::FPC, c);
+        run("duo<float,16,0,MINB=3>", stft_psd_duo_kernel<float, 16, 0>, DP::NT, DP::SMEM, DP::FPC, c);
     } else if (HOP == 256) {
         run("warp<9,float,8,0>", stft_psd_warp_kernel<9, float, 8, 0>, WP::NT, WP::SMEM, WP::FPC, c);
         run("duo<float,8,0,MINB=3>", stft_psd_duo_kernel<float, 8, 0>, DP::NT, DP::SMEM, DP::FPC, c);
