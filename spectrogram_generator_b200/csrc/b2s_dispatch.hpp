@@ -51,11 +51,12 @@ inline int sliding_shift(const StftArgs& a, int log2n) {
 
 // frame-duo kernel: nperseg 512, hop = S * 32 samples, S in {2, 4, 8}
 inline int duo_slots(const StftArgs& a, int log2n) {
-    if (log2n != 9 || !frames_vec_aligned(a) || a.hop % 32) return 0;
-    const long long s = a.hop / 32;
+    if (log2n != 9 || !frames_vec_aligned(a)) return 0;
     // 14, 16: hop = 7/8 nperseg (the reference's default overlap) and hop = nperseg -- the register window
-    // holds both frames whole; measured 71 -> 84 % and 76 -> 88 % of the HBM peak against the warp kernel
-    return (s == 2 || s == 4 || s == 8 || s == 14 || s == 16) ? (int)s : 0;
+    // holds both frames whole; measured 71 -> 84 % and 76 -> 88 % of the HBM peak against the warp kernel.
+    // Any other (even) hop takes the S = 16 variant too: it loads both frames afresh wherever B starts.
+    const long long s = (a.hop % 32) ? 16 : a.hop / 32;
+    return (s == 2 || s == 4 || s == 8 || s == 14) ? (int)s : 16;
 }
 
 template <typename Tin, int MODE, class Launcher>
@@ -83,8 +84,7 @@ int dispatch_warp_shift(const StftArgs& a, Launcher& L, int shift) {
                 case 128: return L.template duo256<Tin, 8, MODE>(a);
                 // 7/8 nperseg (the reference's default overlap) and no overlap: 51 -> 74 %, 62 -> 77 % of the HBM peak
                 case 224: return L.template duo256<Tin, 14, MODE>(a);
-                case 256: return L.template duo256<Tin, 16, MODE>(a);
-                default: break;
+                default: return L.template duo256<Tin, 16, MODE>(a);        // no overlap, and any other even hop
             }
         }
     }

@@ -41,6 +41,9 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
     constexpr int M = DP::M, G = DP::G, ROW = DP::ROW;
     constexpr int NCUR = 16 + S;
     constexpr int KEEP = (NCUR > 2 * S) ? NCUR - 2 * S : 0;
+    // S == 16 keeps both frames of a duo whole, so it serves ANY hop (up to nperseg): frame B's slots
+    // then start hop samples after frame A's instead of exactly 16 slots (256 samples) after
+    const long long bskew = (S == 16) ? (long long)p.hop - 16 * 16 : 0;
     static_assert(PL::NS == 16 && PL::GF == 8, "plan tables: FIN = W_128^(r kappa)");
 
     B2S_DYN_SMEM_F4(sm4);
@@ -102,7 +105,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
         float2 cur[NCUR];
         {
             const Tin* const xf = xb + (long long)f_begin * p.hop;
-            const Tin* const xfB = xf - ((f_begin + 1 < f_end) ? 0 : p.hop);
+            const Tin* const xfB = xf + bskew - ((f_begin + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
             for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xf : xfB) + 16 * i);
         }
@@ -205,7 +208,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
                 for (int i = 0; i < KEEP; ++i) cur[i] = cur[i + 2 * S];
                 const int fa = (f + 2 < f_end) ? f + 2 : f_end - 1;
                 const Tin* const xn = xb + (long long)fa * p.hop;
-                const Tin* const xnB = xn - ((fa + 1 < f_end) ? 0 : p.hop);
+                const Tin* const xnB = xn + bskew - ((fa + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
                 for (int i = KEEP; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xn : xnB) + 16 * i);
             }

@@ -178,6 +178,9 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
     constexpr int M = DP::M, G = DP::G, ROW = DP::ROW;
     constexpr int NCUR = 16 + S;                         // raw complex slots of the duo
     constexpr int KEEP = (NCUR > 2 * S) ? NCUR - 2 * S : 0;   // slots shared with the next duo
+    // S == 16 keeps both frames of a duo whole, so it serves ANY hop (up to nperseg): frame B's slots
+    // then start hop samples after frame A's instead of exactly 16 slots (512 samples) after
+    const long long bskew = (S == 16) ? (long long)p.hop - 16 * 32 : 0;
 
     B2S_DYN_SMEM_F4(sm4);
     const int tid = (int)threadIdx.x;
@@ -240,7 +243,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
         float2 cur[NCUR];
         {
             const Tin* const xf = xb + (long long)f_begin * p.hop + 2 * t;
-            const Tin* const xfB = xf - ((f_begin + 1 < f_end) ? 0 : p.hop);
+            const Tin* const xfB = xf + bskew - ((f_begin + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
             for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xf : xfB) + 32 * i);
         }
@@ -312,7 +315,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, MINB) stft_psd_duo_kernel(const S
                 for (int i = 0; i < KEEP; ++i) cur[i] = cur[i + 2 * S];
                 const int fa = (f + 2 < f_end) ? f + 2 : f_end - 1;
                 const Tin* const xn = xb + (long long)fa * p.hop + 2 * t;
-                const Tin* const xnB = xn - ((fa + 1 < f_end) ? 0 : p.hop);
+                const Tin* const xnB = xn + bskew - ((fa + 1 < f_end) ? 0 : p.hop);
 #pragma unroll
                 for (int i = KEEP; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xn : xnB) + 32 * i);
             }

@@ -191,13 +191,13 @@ def test_fused_band_power(emu, nperseg):
     np.testing.assert_allclose(band, So[:, kmin:kmax + 1, :].sum(axis=1), rtol=1e-5)
 
 
-@pytest.mark.parametrize("nperseg,hop", [(512, 64), (512, 128), (512, 256), (512, 448), (512, 512),
-                                         (256, 32), (256, 64), (256, 128), (256, 224), (256, 256)])
+@pytest.mark.parametrize("nperseg,hop", [(512, 64), (512, 128), (512, 256), (512, 448), (512, 512), (512, 300), (512, 10),
+                                         (256, 32), (256, 64), (256, 128), (256, 224), (256, 256), (256, 100)])
 @pytest.mark.parametrize("nframes_extra", [0, 1])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_frame_duo_kernel(emu, nperseg, hop, nframes_extra, detrend):
-    """nperseg 512 (hop 64/128/256) and 256 (hop 32/64/128) run on the packed two-frames-per-lane
-    kernels: odd and even frame counts, runs cut at odd lengths, crop / frame range / band power,
+    """nperseg 512 and 256 with any even hop run on the packed two-frames-per-lane kernels (sliding
+    register window for hop = nperseg/8, /4, /2 and 7/8 nperseg, both frames loaded whole otherwise): odd and even frame counts, runs cut at odd lengths, crop / frame range / band power,
     float64 samples, against the oracle; the result of a frame must not depend on the chunking."""
     nfr = 6 + nframes_extra
     n = nperseg + hop * (nfr - 1) + 6          # even rows: the packed kernels need 8-byte aligned frames

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 # (nperseg, hop) -> family that runs it
 CASES = [
     (512, 128), (512, 64), (512, 256), (512, 512),        # frame-duo kernel ((512, 448) below: even rows permitting)
-    (256, 64), (256, 32), (256, 128), (256, 224), (256, 256),   # frame-duo kernel, 8 lanes (224: even rows permitting)
+    (256, 64), (256, 32), (256, 128), (256, 224), (256, 256), (256, 100),   # frame-duo kernel, 8 lanes (even rows permitting)
+    (512, 300), (512, 10),                                # frame-duo kernel, any even hop
     (1024, 256), (1024, 128), (1024, 512),                # four-step duo, R = 2
     (1024, 1024),                                         # four-step duo without overlap (1024/896 below: odd rows permitting)
     (2048, 512), (2048, 1024), (4096, 1024), (4096, 512), # four-step duo, R = 4 / 8

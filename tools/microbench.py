@@ -68,6 +68,9 @@ def main():
             shapes.append((1000, 200_000, nperseg, nperseg - nperseg // 8, ("tukey", .25)))
         for nperseg in (256, 512, 1024):
             shapes.append((1000, 200_000 // nperseg * nperseg, nperseg, nperseg, "hann"))
+    if args.set == "anyhop":        # hops outside the sliding-window sets (B2S_NO_DUO=1 gives the warp kernel for comparison)
+        shapes += [(1000, 200_000, 512, 300), (1000, 200_000, 512, 384), (1000, 200_000, 512, 100),
+                   (1000, 200_000, 256, 192), (1000, 200_000, 256, 100)]
     if args.set == "n1024ref":      # nperseg 1024 at the reference's default overlap and without overlap
         shapes += [(1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 1024, 896),
                    (1000, 40960, 1024, 1024)]
