@@ -144,3 +144,28 @@ def test_fused_sum_matches_the_two_pass_sum_and_the_public_mean(monkeypatch):
     f, t, m = sg.mean_spectrogram(x, fs=fs, **kw)
     _, _, mo = stft_oracle.mean_spectrogram(x.astype(np.float64), fs=fs, **kw)
     assert_parity(m, mo, what="mean spectrogram through the sum-fused kernel")
+
+
+def test_odd_row_lengths_through_the_host_api_take_the_packed_kernels():
+    """A batch with an odd number of samples per row: the host API stages it into rows of even stride
+    (same bits as handing the engine such rows); a device-resident batch with an odd row stride runs the
+    scalar-load kernels; both match the oracle."""
+    rng = np.random.default_rng(77)
+    n = 512 + 128 * 9 + 1
+    x = _signal(rng, 3, n, dc=-3.0)
+    kw = dict(window="hann", nperseg=512, noverlap=384)
+    plan = sg.triage(n, 20000.0, "hann", 512, 384, None, "constant", True, "density", "psd")
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    assert xd.stride(0) % 2 == 1
+    scalar = eng.stft_psd(xd, plan)
+    wide = torch.zeros((3, n + 1), dtype=torch.float32, device="cuda")
+    wide[:, :n] = xd
+    packed = eng.stft_psd(wide[:, :n], plan)
+    assert_parity(np.moveaxis(scalar.cpu().numpy(), -1, -2), So, what="odd rows, scalar loads")
+    assert_parity(np.moveaxis(packed.cpu().numpy(), -1, -2), So, what="odd rows staged at even stride")
+    f, t, S = sg.spectrogram(x, fs=20000.0, **kw)
+    assert np.array_equal(np.moveaxis(S, -1, -2), packed.cpu().numpy())
+    f, t, m, Sm = sg.mean_spectrogram(x, fs=20000.0, return_per_sweep=True, **kw)
+    assert np.array_equal(np.moveaxis(Sm, -1, -2), packed.cpu().numpy())
