@@ -68,6 +68,9 @@ def main():
             shapes.append((1000, 200_000, nperseg, nperseg - nperseg // 8, ("tukey", .25)))
         for nperseg in (256, 512, 1024):
             shapes.append((1000, 200_000 // nperseg * nperseg, nperseg, nperseg, "hann"))
+    if args.set == "small":         # nperseg <= 128 (warp kernel)
+        shapes += [(1000, 200_000, 128, 112, ("tukey", .25)), (1000, 200_000, 128, 32), (1000, 200_000, 64, 56, ("tukey", .25)),
+                   (1000, 200_000, 32, 28, ("tukey", .25))]
     if args.set == "anyhop":        # hops outside the sliding-window sets (B2S_NO_DUO=1 gives the warp kernel for comparison)
         shapes += [(1000, 200_000, 512, 300), (1000, 200_000, 512, 384), (1000, 200_000, 512, 100),
                    (1000, 200_000, 256, 192), (1000, 200_000, 256, 100)]
