@@ -239,11 +239,13 @@ def run_gpu(args):
             return mean_buf
         return eng.batch_sum(S, 1.0 / total_sweeps, out=mean_buf)
 
+    peer_out = [torch.empty(plan.nframes * plan.nbins, dtype=torch.float32, device=dev) for _ in range(4)]
+
     def reduce_mean():
         if peer is not None:
             if not fused:
                 eng.batch_sum(S, 1.0, out=peer.partial())
-            return peer.reduce(1.0 / total_sweeps)
+            return peer.reduce(1.0 / total_sweeps, out=peer_out[peer.epoch & 3])
         mean = partial_mean()                            # partial mean of this rank's sweeps
         if world > 1 and mode == "sync":
             dist.all_reduce(mean)                        # sum of partial means == global mean
@@ -267,6 +269,7 @@ def run_gpu(args):
     sampler.start()
     start.record()
     pending = []
+    t_host = time.perf_counter()
     for i in range(args.steps):
         k_ev[i][0].record()
         spectrograms()
@@ -281,6 +284,7 @@ def run_gpu(args):
     if peer is not None:
         peer.wait()                  # overlap mode: the side stream's reduces join the timed stream
     end.record()
+    host_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # host time to enqueue one step
     sampler.sample()                 # all K steps are enqueued: this sample is taken under load
     torch.cuda.synchronize()
     if world > 1:
@@ -345,7 +349,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sweeps_per_gpu": B, "global_sweeps": total_sweeps,
                        "frames_per_sweep": F, "bins": K,
-                       "allreduce_check": check,
+                       "allreduce_check": check, "host_enqueue_ms_per_step": round(host_ms, 4),
                        "l2": "inputs+outputs per step (478 MB) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"sweeps sharded, {world} rank(s); all_reduce of the [F,K] partial sum only "
                                       f"({collective}, in stream order after the cross-sweep sum, inside the timed region)"},

@@ -197,6 +197,10 @@ class PeerMeanReducer:
         if self.overlap:
             with torch.cuda.device(self.device):
                 self.side = torch.cuda.Stream(priority=-1)       # its few CTAs go first when slots free up
+                # events are reused round-robin (a wait captures the record that precedes it): the step
+                # loop must stay cheap on the host, one step is ~0.17 ms of GPU time
+                self._ev_ready = [torch.cuda.Event() for _ in range(4)]
+                self._ev_done = [torch.cuda.Event() for _ in range(4)]
         self.handle.barrier()                  # pads and buffers exist on every rank before the first kernel
 
     def _slot(self, epoch: int) -> int:
@@ -220,6 +224,7 @@ class PeerMeanReducer:
         next-but-one ``partial()``) joins it."""
         self.epoch += 1
         k = self._slot(self.epoch)
+        caller_out = out is not None       # the caller keeps it alive until wait() (overlap mode)
         if out is None:
             out = torch.empty(self.elems, dtype=torch.float32, device=self.device)
         bufs = (self._ct.c_ulonglong * self.world)(*[b + 4 * k * self.stride for b in self._bufs])
@@ -227,7 +232,7 @@ class PeerMeanReducer:
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             if self.overlap:
-                ready = torch.cuda.Event()
+                ready = self._ev_ready[self.epoch & 3]
                 ready.record(cur)
                 self.side.wait_event(ready)
                 stream = self.side
@@ -237,8 +242,9 @@ class PeerMeanReducer:
                                                   out.data_ptr(), float(post_scale), stream.cuda_stream)
             _lib.check(rc, "b2s_peer_allreduce_f32")
             if self.overlap:
-                out.record_stream(self.side)
-                done = torch.cuda.Event()
+                if not caller_out:
+                    out.record_stream(self.side)
+                done = self._ev_done[self.epoch & 3]
                 done.record(self.side)
                 self._done[self.epoch] = done
         return out
