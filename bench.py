@@ -337,9 +337,9 @@ def run_gpu(args):
         achieved = bytes_alg / (kern_ms * 1e-3) / 1e9
         cpu_v, cpu_cores, cpu_dt = cpu_baseline_leg(x_host, kw, all_cores=False) if world == 1 else (None, None, None)
         if fused:
-            kernel_name = ("stft_psd_duo_sum_kernel<float,S=4> (nperseg 512, hop 128: two frames per lane group, packed "
-                           "fp32x2, walks a block of sweeps and keeps their running sum in shared memory); kernel_ms "
-                           "brackets this launch plus the ~5 us fold of its 22 partial sums")
+            kernel_name = ("stft_psd_duo_sum_kernel<float,S=4,ACC_TMEM=1> (nperseg 512, hop 128: two frames per lane "
+                           "group, packed fp32x2, walks a block of sweeps and keeps their running sums in tensor "
+                           "memory); kernel_ms brackets this launch plus the ~5 us fold of its 22 partial sums")
         else:
             kernel_name = ("stft_psd_duo_kernel<float,S=4,EPI_PLAIN> (nperseg 512, hop 128: two frames per lane group, "
                            "packed fp32x2)")
