@@ -312,3 +312,27 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend):
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:501])
     band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
+
+
+def test_sum_fused_plan_properties():
+    """plan_stft_sum over random shapes: the blocks cover every sweep exactly once (ragged last
+    block only), never exceed the cap, and the unit count matches blocks x even duo slots."""
+    import ctypes
+    import __graft_entry__ as ge
+    lib = ctypes.CDLL(ge.build_emulator())
+    fn = lib.emu_plan_sum
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    o = (ctypes.c_longlong * 3)()
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        batch = int(rng.integers(1, 5000))
+        nframes = int(rng.integers(1, 2000))
+        resident = int(rng.integers(1, 5000))
+        cap = int(rng.integers(1, 65))
+        blocks = fn(batch, nframes, resident, cap, o)
+        rows, ups, units = o[0], o[1], o[2]
+        assert 1 <= blocks <= min(cap, batch)
+        assert (blocks - 1) * rows < batch <= blocks * rows
+        nduos = (nframes + 1) // 2
+        assert ups == (nduos + 1) // 2 * 2 and units == blocks * ups
