@@ -86,35 +86,67 @@ struct KernelState {
 };
 std::map<const void*, KernelState> g_kern;     // guarded by g_mu
 
-// One launch of an STFT kernel (either family): persistent grid sized from the
-// occupancy, work units sized from the grid (b2s::plan_stft).
-// Work counters for the dynamically scheduled kernels: a ring of (next unit, CTAs done) pairs per
-// device, zero when idle (the last CTA of a launch re-arms its pair).  The ring is long enough
-// that a pair is not handed out again while a launch that uses it can still be in flight; if it
-// ever were, units would only be processed twice (the stores are idempotent), never skipped.
-constexpr int kWorkRing = 1024;
-std::map<int, int*> g_work;                    // guarded by g_mu
-std::map<int, unsigned> g_work_next;           // guarded by g_mu
+// Work counters of the dynamically scheduled kernels: one (next unit, CTAs done) pair per
+// (device, stream), zero when idle -- the last CTA of a launch re-arms its pair, and launches of one
+// stream do not overlap, so a pair is never shared by two launches in flight.  A launch that is
+// being captured into a CUDA graph takes the static schedule instead (a replayed graph may run
+// beside eager launches of the stream it was captured on).
+std::map<std::pair<int, cudaStream_t>, int*> g_work;     // guarded by g_mu
 
-int work_counters(int dev, int** out) {
+int work_counters(int dev, cudaStream_t stream, int** out) {
     std::lock_guard<std::mutex> g(g_mu);
-    auto it = g_work.find(dev);
+    auto key = std::make_pair(dev, stream);
+    auto it = g_work.find(key);
     if (it == g_work.end()) {
         int* d = nullptr;
-        cudaError_t e = cudaMalloc(&d, 2 * kWorkRing * sizeof(int));
+        cudaError_t e = cudaMalloc(&d, 32 * sizeof(int));       // one 128-byte line per stream
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(work counters)");
-        e = cudaMemset(d, 0, 2 * kWorkRing * sizeof(int));
+        e = cudaMemsetAsync(d, 0, 32 * sizeof(int), stream);    // ordered before the first launch that uses it
         if (e != cudaSuccess) {
             cudaFree(d);
-            return cuda_fail(e, "cudaMemset(work counters)");
+            return cuda_fail(e, "cudaMemsetAsync(work counters)");
         }
-        it = g_work.emplace(dev, d).first;
-        g_work_next[dev] = 0;
+        it = g_work.emplace(key, d).first;
     }
-    *out = it->second + 2 * (g_work_next[dev]++ % kWorkRing);
+    *out = it->second;
     return B2S_OK;
 }
 
+bool stream_capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// diagnostic switches, read once per process
+struct EnvSwitches {
+    bool allow_duo = true, duo1024 = true, allow_duo4 = true, allow_big = true, dynamic_units = true;
+    bool allow_pair = true, fused_sum = true, sum_acc_smem = false;
+    int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
+    EnvSwitches() {
+        auto on = [](const char* name) { const char* v = getenv(name); return v && atoi(v) != 0; };
+        auto off0 = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) != 0 : dflt; };
+        allow_duo = !on("B2S_NO_DUO");
+        duo1024 = off0("B2S_DUO1024", true);
+        allow_duo4 = !on("B2S_NO_DUO4");
+        allow_big = !on("B2S_NO_BIG");
+        dynamic_units = !on("B2S_STATIC_UNITS");
+        allow_pair = !on("B2S_NO_PAIR");
+        fused_sum = !on("B2S_NO_FUSED_SUM");
+        sum_acc_smem = on("B2S_SUM_ACC_SMEM");
+        if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
+    }
+};
+const EnvSwitches& env() {
+    static const EnvSwitches e;
+    return e;
+}
+
+// One launch of an STFT kernel (either family): persistent grid sized from the
+// occupancy, work units sized from the grid (b2s::plan_stft).
 int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
                     bool direct_table = false, bool dynamic = false) {
     DeviceInfo di;
@@ -145,12 +177,12 @@ int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::S
     std::string err;
     // small launches (less than ~4 duos per resident group) keep the static schedule: the two
     // counter round trips cost more than any imbalance they could remove
-    dynamic = dynamic && (a.batch * a.nframes >= 8 * resident_ctas * fpc);
+    dynamic = dynamic && (a.batch * a.nframes >= 8 * resident_ctas * fpc) && !stream_capturing(stream);
     rc = b2s::plan_stft(a, fpc, resident_ctas * fpc, p, err, dynamic);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
     if (dynamic) {
-        rc = work_counters(dev, &p.work);
+        rc = work_counters(dev, stream, &p.work);
         if (rc != B2S_OK) return rc;
     }
     rc = twiddles(dev, a.nperseg, direct_table, &p.tw);
@@ -161,6 +193,60 @@ int launch_any_impl(const void* kern, int nt, size_t smem, int fpc, const b2s::S
     void* args[] = {&p};
     cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)nt), args, smem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "stft kernel launch");
+    return B2S_OK;
+}
+
+// the staged-sample pair kernel (b2s_pair_kernel.cuh): shared memory -- hence residency -- depends on the hop
+struct PairState {
+    int occ = 0;
+    int max_smem = 0;
+};
+std::map<std::pair<const void*, long long>, PairState> g_pair;     // (kernel, device << 32 | smem) -> residency
+
+int launch_pair_impl(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
+    using PP = b2s::PairPlan<10>;
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const size_t smem = PP::smem_bytes(a.hop, esz);
+    if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this hop");
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        PairState& ks = g_pair[std::make_pair(kern, ((long long)dev << 32) | (long long)smem)];
+        if (ks.occ == 0) {
+            // the attribute is the maximum any launch of this kernel may ask for
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, PP::NT, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            if (ks.occ < 1) ks.occ = 1;
+        }
+        occ = ks.occ;
+    }
+    const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
+    const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
+    const long long resident_warps = resident_ctas * PP::FPC;
+    b2s::StftParams p{};
+    std::string err;
+    dynamic = dynamic && (a.batch * a.nframes >= 16 * resident_warps) && !stream_capturing(stream);
+    rc = b2s::plan_stft(a, PP::FPC, resident_warps, p, err, dynamic);
+    if (rc < 0) return fail(rc, err);
+    if (p.n_units == 0) return B2S_OK;
+    b2s::plan_pair_units(a, resident_warps, env().pair_units, dynamic, p);
+    p.ring = PP::ring_samples(a.hop);
+    if (dynamic) {
+        rc = work_counters(dev, stream, &p.work);
+        if (rc != B2S_OK) return rc;
+    }
+    rc = twiddles(dev, a.nperseg, false, &p.tw);
+    if (rc != B2S_OK) return rc;
+    const long long need = (p.n_units + PP::FPC - 1) / PP::FPC;
+    const long long grid = (need < resident_ctas) ? need : resident_ctas;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)PP::NT), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pair stft kernel launch");
     return B2S_OK;
 }
 
@@ -212,11 +298,13 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     }
     if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
     b2s::CudaLauncher L{(cudaStream_t)stream};
-    if (const char* v = getenv("B2S_NO_DUO")) L.allow_duo = (atoi(v) == 0);
-    if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
-    if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
-    if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
-    if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
+    const EnvSwitches& sw = env();
+    L.allow_duo = sw.allow_duo;
+    L.duo1024 = sw.duo1024;
+    L.allow_duo4 = sw.allow_duo4;
+    L.allow_big = sw.allow_big;
+    L.dynamic_units = sw.dynamic_units;
+    L.allow_pair = sw.allow_pair && sw.allow_duo;
     // the reference's call (linear power, every bin) takes the branch-free epilogue
     const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
     const int mode = a.band_mode ? b2s::EPI_BAND : (general ? b2s::EPI_GENERAL : b2s::EPI_PLAIN);
@@ -239,8 +327,7 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-    const char* smem_acc = getenv("B2S_SUM_ACC_SMEM");
-    const int tmem = (smem_acc && atoi(smem_acc)) ? 0 : 1;
+    const int tmem = env().sum_acc_smem ? 0 : 1;
     const void* twin = b2s::duo_sum_kernel_for(a.x_is_f64, slots, 0);
     const void* kern = tmem ? b2s::duo_sum_kernel_for(a.x_is_f64, slots, 1) : twin;
     if (!kern || !twin) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
@@ -302,9 +389,7 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     if (!sum_out || !scratch) return fail(B2S_ERR_BAD_ARG, "b2s_stft_psd_sum: sum_out and scratch are required");
     if (nframes < 1 || batch < 1) return fail(B2S_ERR_BAD_ARG, "b2s_stft_psd_sum: nothing to sum");
     const long long elems = nframes * (nperseg / 2 + 1);
-    const char* off = getenv("B2S_NO_FUSED_SUM");
-    const char* noduo = getenv("B2S_NO_DUO");
-    int slots = ((off && atoi(off)) || (noduo && atoi(noduo)) || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
+    int slots = (!env().fused_sum || !env().allow_duo || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
     if (slots > 8) slots = 0;           // hop 448 / 512: per-sweep frame-duo kernel, no sum-fused variant
     if (slots) return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
     // every other shape: the per-sweep kernel of its family, then the two-pass sum
@@ -319,6 +404,10 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
 int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
                    bool dynamic) {
     return launch_any_impl(kern, nt, smem, fpc, a, stream, false, dynamic);
+}
+
+int b2s_launch_pair(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
+    return launch_pair_impl(kern, esz, a, stream, dynamic);
 }
 
 extern "C" {

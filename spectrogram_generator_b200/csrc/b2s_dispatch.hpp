@@ -14,6 +14,8 @@
 //   template <typename Tin, int S, int MODE>                int duo256(const StftArgs&);
 //   template <int LOG2N, typename Tin, int MODE>            int big(const StftArgs&);   (8192, 16384)
 //   bool allow_big;
+//   template <int LOG2N, typename Tin, int MODE>            int pair(const StftArgs&);  (1024, staged samples)
+//   bool allow_pair;
 //   bool allow_duo, duo1024, allow_duo4;
 //
 //   nperseg == 512 with hop in {64, 128, 256, 448, 512} (2-element aligned frames) takes the packed
@@ -31,6 +33,7 @@
 #include "b2s_duo4_kernel.cuh"
 #include "b2s_duo_cta_kernel.cuh"
 #include "b2s_duo_kernel.cuh"
+#include "b2s_pair_kernel.cuh"
 #include "b2s_warp_kernel.cuh"
 
 namespace b2s {
@@ -142,6 +145,10 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
         case 8: return dispatch_warp_shift<8, Tin, MODE>(a, L, shift);
         case 9: return dispatch_warp_shift<9, Tin, MODE>(a, L, shift);
         case 10:
+            // staged-sample pair kernel: any hop that keeps the frames 16-byte aligned
+            if (L.allow_pair && pair_kernel_ok(a.x, a.x_is_f64, a.batch, a.x_batch_stride, a.nperseg, a.hop, a.frame0) &&
+                reinterpret_cast<uintptr_t>(a.window) % 16 == 0)
+                return L.template pair<10, Tin, MODE>(a);
             if (L.allow_duo && L.duo1024) return dispatch_duo_big<10, Tin, MODE>(a, L);
             return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
         case 11: return L.allow_duo ? dispatch_duo_big<11, Tin, MODE>(a, L) : L.template cta<11, Tin, MODE>(a);

@@ -168,6 +168,28 @@ inline int plan_stft(const StftArgs& a, int groups_per_cta, long long resident_g
     return log2n;
 }
 
+// Work units of the staged-sample pair kernel (b2s_pair_kernel.cuh): one run per warp at a time.  A run
+// starts by staging nperseg + hop samples, so runs are longer than the other families' (about
+// `units_per_warp` runs per resident warp) and a signal is cut into runs of equal, even length.
+inline void plan_pair_units(const StftArgs& a, long long resident_warps, int units_per_warp, bool dynamic,
+                            StftParams& p) {
+    if (units_per_warp <= 0) units_per_warp = dynamic ? 4 : 2;
+    if (resident_warps < 1) resident_warps = 1;
+    const long long total = a.batch * a.nframes;
+    const long long want = resident_warps * units_per_warp;
+    long long cf = (total + want - 1) / want;
+    if (cf < 4) cf = 4;
+    if (cf > 512) cf = 512;
+    if (cf > a.nframes) cf = a.nframes > 0 ? a.nframes : 1;
+    long long ups = (a.nframes + cf - 1) / cf;
+    if (ups < 1) ups = 1;
+    cf = (a.nframes + ups - 1) / ups;
+    if (cf & 1) ++cf;
+    p.chunk_frames = (int)cf;
+    p.units_per_signal = (a.nframes + cf - 1) / cf;
+    p.n_units = p.units_per_signal * a.batch;
+}
+
 // Work units of the sum-fused frame-duo kernel (b2s_duo_sum_kernel.cuh): a unit is one frame duo
 // over a block of `rows` consecutive sweeps, so every unit costs the same and the static
 // round-robin is balanced when the units fill the resident lane groups a whole number of times.

@@ -1,0 +1,11 @@
+// kernel instantiations: the staged-sample pair kernel (b2s_pair_kernel.cuh) is instantiated through
+// dispatch_tg in the b2s_inst_f32_* / b2s_inst_f64_* units; this unit only checks at compile time that
+// the bulk-copy path builds for both sample types with the plain epilogue.
+#include "b2s_launcher.hpp"
+
+namespace b2s {
+const void* pair_kernel_probe(int x_is_f64) {
+    return x_is_f64 ? (const void*)stft_psd_pair_kernel<10, double, EPI_PLAIN>
+                    : (const void*)stft_psd_pair_kernel<10, float, EPI_PLAIN>;
+}
+}  // namespace b2s

@@ -50,6 +50,7 @@ struct StftParams {
     int out_mode;                // 0 linear power, 1 dB
     int kmin, kmax;              // inclusive bin crop
     int vec_ok;                  // 1: frame starts are 2-element aligned (vector loads)
+    int ring;                    // pair kernel (b2s_pair_kernel.cuh): samples per warp ring in shared memory
     float scale;                 // 1/(fs*sum(w^2))  or  1/sum(w)^2
     float db_floor;              // linear floor applied before log10 in dB mode
 };

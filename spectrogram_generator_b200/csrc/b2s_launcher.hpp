@@ -13,6 +13,9 @@
 int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
                    bool dynamic = false);
 
+// One launch of the staged-sample pair kernel (b2s_pair_kernel.cuh).  Defined in b2s_api.cu.
+int b2s_launch_pair(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic);
+
 namespace b2s {
 
 struct CudaLauncher {
@@ -21,6 +24,12 @@ struct CudaLauncher {
     bool duo1024 = true;
     bool allow_duo4 = true;
     bool allow_big = true;
+    bool allow_pair = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int pair(const StftArgs& a) {
+        return b2s_launch_pair((const void*)stft_psd_pair_kernel<LOG2N, Tin, MODE>, (int)sizeof(Tin), a, stream,
+                               dynamic_units);
+    }
     template <int LOG2N, typename Tin, int MODE>
     int big(const StftArgs& a) {
         using BP = BigPlan<LOG2N>;

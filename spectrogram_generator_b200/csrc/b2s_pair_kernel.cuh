@@ -1,0 +1,494 @@
+// Sub-sequence-pair STFT -> PSD kernel for nperseg 1024 (any hop that is a multiple of 4
+// samples), samples staged through shared memory by the bulk-copy engine (TMA).
+//
+// The frame-duo kernels pack two FRAMES in fp32x2 registers and keep the raw samples of the
+// overlapping frames in a sliding register window; at nperseg >= 1024 that window (40 registers),
+// the strided sample loads and the group-wide exchanges make them LSU-bound
+// (profiles/r1_c3_duo4_v11.ncu_summary.txt).  This kernel packs two SUB-TRANSFORMS of ONE frame:
+//
+//   the frame's N = 1024 real samples are four real sub-sequences x_r[m] = x[4 m + r] of 256
+//   points.  z_A = x_0 + i x_2 and z_B = x_1 + i x_3 are transformed together, A in the low and B
+//   in the high halves of fp32x2 registers: both use the SAME pass-0 / pass-1 twiddles (broadcast
+//   scalars, as in the frame-duo kernels), and the four samples x[4 m .. 4 m + 3] of a point are
+//   ONE 16-byte word whose register quad is already (re_A, re_B | im_A, im_B) -- no shuffling of
+//   registers, window taps in natural order.  16 lanes own a frame, lane t slot i holds
+//   m = t + 16 i; the 16 lanes read 256 contiguous bytes: conflict-free LDS.128 straight from the
+//   staged samples, with any hop.
+//   * one 16 x 16 transpose per frame through a buffer private to the half-warp (__syncwarp only);
+//   * the mirror F[256 - kap] comes from lane (16 - t) & 15 with 32 shuffles; with it the fused
+//     final stage untangles the four real spectra (2 X_0, 2 X_1 = F + conj(F'), 2 X_2, 2 X_3 =
+//     -i (F - conj(F'))), applies W_1024^(r kap) and one radix-4 butterfly gives the bins kap,
+//     kap + 256, 256 - kap and 512 - kap -- real-FFT split and last radix in one step;
+//   * no group-wide barrier anywhere: the two frames of a warp only share instructions.
+//
+// Sample staging (north-star kernel 1): every warp owns a ring of N + hop samples in shared
+// memory.  Lane 0 feeds it with cp.async.bulk (global -> shared, completion on an mbarrier):
+// the first N + hop samples of a run of frames, then 2 hop new samples per pair of frames,
+// issued as soon as the pair before has read its samples -- a whole iteration ahead of their
+// use, with no registers and no LSU instructions spent on global loads.  Every sample of a run
+// crosses L2 -> SM once.  The ring of the next run is primed during the last iteration of the
+// current one (units are drawn one ahead).
+//
+// Detrend: coarse mean, then the mean of the residual, in a fixed frame-relative order (the
+// result of a frame depends on its samples only).  float64 samples are staged as float64 and the
+// coarse mean is subtracted in double before the cast, so a recording that sits on a large DC
+// level keeps its small signal (SciPy detrends float64 input in float64).
+#pragma once
+
+#include "b2s_duo_cta_kernel.cuh"
+
+namespace b2s {
+
+template <int LOG2N>
+struct PairPlan {
+    using PL = Plan<LOG2N>;
+    static constexpr int N = PL::N, M = PL::M;
+    static constexpr int R = M / 256;
+    static_assert(R == 2, "pair kernel: nperseg 1024 (four real sub-sequences of 256 points)");
+    static constexpr int NT = 128;                       // threads per CTA
+    static constexpr int NW = NT / 32;                   // warps = rings per CTA
+    static constexpr int NHW = NT / 16;                  // frames in flight per CTA
+    static constexpr int FPC = NW;                       // work units in flight per CTA (one run per warp)
+    static constexpr int ROW = 17, BUF = 16 * ROW;       // transpose buffer of one frame, float4 units
+    // shared memory, float4 units
+    static constexpr int OFF_WIN = 0;                    // [16][16] taps of slot i, lane t: w[4 (t + 16 i) .. + 3] * sqrt(scale/2)
+    static constexpr int OFF_TW1 = OFF_WIN + 16 * 16;    // [8][16] W_256^(t' q), t' = 2j, 2j+1
+    static constexpr int OFF_W12 = OFF_TW1 + 8 * 16;     // [8][16] (W_1024^kap, W_1024^(2 kap)), kap = t + 16 pp
+    static constexpr int OFF_W3 = OFF_W12 + 8 * 16;      // [8][16] float2 W_1024^(3 kap)  (half a float4 each)
+    static constexpr int OFF_BUF = OFF_W3 + 4 * 16;
+    static constexpr int OFF_BAR = OFF_BUF + NHW * BUF;  // NW x 2 mbarriers (one float4 per warp)
+    static constexpr int OFF_RING = OFF_BAR + NW;        // NW rings of ring_samples elements each
+    // ring: the N + hop samples of a pair of frames, rounded up to 128 bytes
+    static int ring_samples(int hop) { return (N + hop + 31) / 32 * 32; }
+    static size_t smem_bytes(int hop, int esz) {
+        return (size_t)OFF_RING * sizeof(float4) + (size_t)NW * ring_samples(hop) * esz;
+    }
+};
+
+// hop must keep every frame start on a 16-byte boundary of the row
+inline bool pair_kernel_ok(const void* x, int x_is_f64, long long batch, long long x_batch_stride, int nperseg, int hop,
+                           long long frame0) {
+    (void)frame0;
+    if (nperseg != 1024) return false;
+    const int per16 = x_is_f64 ? 2 : 4;                  // samples per 16 bytes
+    if (reinterpret_cast<uintptr_t>(x) % 16) return false;
+    if (hop % 4 || hop < 32 || hop > nperseg) return false;
+    if (batch > 1 && (x_batch_stride % per16)) return false;
+    return true;
+}
+
+#ifdef B2S_EMU
+#define B2S_SCHED_FENCE() do {} while (0)
+#else
+// keeps the compiler from hoisting every load of an unrolled loop above their uses (register pressure)
+#define B2S_SCHED_FENCE() asm volatile("" ::: "memory")
+#endif
+
+// ---- bulk-copy / mbarrier primitives -----------------------------------------------------------
+#ifdef B2S_EMU
+struct RingBar { int dummy; };
+B2S_DEVICE void ring_bar_init(void*, int) {}
+B2S_DEVICE void ring_fence_init() {}
+B2S_DEVICE void ring_expect(void*, unsigned) {}
+B2S_DEVICE void ring_copy(void* dst, const void* src, unsigned bytes, void*) { std::memcpy(dst, src, bytes); }
+B2S_DEVICE void ring_wait(void*, unsigned) {}
+#else
+B2S_DEVICE unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+B2S_DEVICE void ring_bar_init(void* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+B2S_DEVICE void ring_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+B2S_DEVICE void ring_expect(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size a multiple of 16
+B2S_DEVICE void ring_copy(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+B2S_DEVICE void ring_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
+// four consecutive samples of the ring as floats; `idx16` counts 16-byte words of float samples
+template <typename Tin> struct RingLoad;
+template <> struct RingLoad<float> {
+    B2S_DEVICE static float4 ld4(const void* ring, int word) { return reinterpret_cast<const float4*>(ring)[word]; }
+};
+template <> struct RingLoad<double> {
+    B2S_DEVICE static float4 ld4(const void* ring, int word) {
+        const double2 a = reinterpret_cast<const double2*>(ring)[2 * word];
+        const double2 b = reinterpret_cast<const double2*>(ring)[2 * word + 1];
+        return make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+    }
+    // (x - pivot) in double, rounded once
+    B2S_DEVICE static float4 ld4_minus(const void* ring, int word, double pivot) {
+        const double2 a = reinterpret_cast<const double2*>(ring)[2 * word];
+        const double2 b = reinterpret_cast<const double2*>(ring)[2 * word + 1];
+        return make_float4((float)(a.x - pivot), (float)(a.y - pivot), (float)(b.x - pivot), (float)(b.y - pivot));
+    }
+};
+
+template <int MODE>
+struct EpiOne {
+    float* row;         // frame row (already offset by -kmin)
+    float floor;
+    float band;
+    int kmin, kmax, db;
+    bool act;
+    B2S_DEVICE void put(int k, float p) {
+        if constexpr (MODE == EPI_GENERAL) {
+            if (db) p = 10.0f * log10f(fmaxf(p, floor));
+            if (act && k >= kmin && k <= kmax) row[k] = p;
+        } else if constexpr (MODE == EPI_BAND) {
+            if (k >= kmin && k <= kmax) band += p;
+        } else {
+            if (act) row[k] = p;
+        }
+    }
+};
+
+template <int LOG2N, typename Tin, int MODE, int MINB = 3>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, MINB) stft_psd_pair_kernel(const StftParams p) {
+    using PL = Plan<LOG2N>;
+    using PP = PairPlan<LOG2N>;
+    constexpr int N = PP::N, M = PP::M, ROW = PP::ROW;
+    constexpr int ESZ = (int)sizeof(Tin);
+
+    B2S_DYN_SMEM_F4(sm4);
+    const int tid = (int)threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int h = lane >> 4;                             // frame of the pair this half-warp owns
+    const int t = lane & 15;
+    float4* const buf = sm4 + PP::OFF_BUF + (tid >> 4) * PP::BUF;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::OFF_BAR + warp);
+    const int RS = p.ring;                               // ring length in samples
+    unsigned char* const ring = reinterpret_cast<unsigned char*>(sm4 + PP::OFF_RING) + (size_t)warp * RS * ESZ;
+
+    // ---- constant tables, once per CTA; the PSD scale goes into the window ----
+    {
+        const float csc = sqrtf(0.5f * p.scale);
+        const float4* w4 = reinterpret_cast<const float4*>(p.window);
+        for (int i = tid; i < 16 * 16; i += PP::NT) {
+            const float4 w = __ldg(w4 + i);             // taps of samples 4 (t + 16 i) .. + 3, i * 16 + t == i
+            sm4[PP::OFF_WIN + i] = make_float4(w.x * csc, w.y * csc, w.z * csc, w.w * csc);
+        }
+        float2* const w3tab = reinterpret_cast<float2*>(sm4 + PP::OFF_W3);
+        for (int i = tid; i < 8 * 16; i += PP::NT) {
+            const int j = i >> 4, l = i & 15;
+            const float2 ta = (j == 0) ? cmk(1.f, 0.f) : __ldg(p.tw + PL::OFF_P1 + (2 * j - 1) * 16 + l);
+            const float2 tb = __ldg(p.tw + PL::OFF_P1 + (2 * j) * 16 + l);
+            sm4[PP::OFF_TW1 + i] = make_float4(ta.x, ta.y, tb.x, tb.y);
+            const int kap = l + 16 * j;                 // final stage, task pp = j of lane l
+            const float2 w1 = __ldg(p.tw + PL::OFF_POST + kap), w2 = __ldg(p.tw + PL::OFF_POST + 2 * kap);
+            sm4[PP::OFF_W12 + i] = make_float4(w1.x, w1.y, w2.x, w2.y);
+            w3tab[i] = __ldg(p.tw + PL::OFF_POST + 3 * kap);
+        }
+        if (lane == 0) {
+            ring_bar_init(bars, 1);
+            ring_bar_init(bars + 1, 1);
+        }
+        ring_fence_init();
+    }
+    __syncthreads();
+
+    const int kout = p.kmax - p.kmin + 1;
+    EpiOne<MODE> epi;
+    epi.floor = p.db_floor;
+    epi.kmin = p.kmin;
+    epi.kmax = p.kmax;
+    epi.db = p.out_mode;
+    epi.band = 0.f;
+    const int partner = (lane & 16) | ((16 - t) & 15);
+    const bool is0 = (t == 0);
+
+    // ---- work units: runs of consecutive frames of one signal, one run per warp at a time ----
+    const bool dyn = p.work != nullptr;
+    auto draw = [&]() -> long long {
+        int b0 = 0;
+        if (lane == 0) b0 = atomicAdd(p.work, 1);
+        return (long long)__shfl_sync(0xffffffffu, b0, 0);
+    };
+    struct Unit {
+        const Tin* x;        // first sample of the run
+        float* out;          // row of the run's first frame (already offset by -kmin)
+        int nf;              // frames in the run
+    };
+    auto unit_of = [&](long long u) -> Unit {
+        const long long b = u / p.units_per_signal;
+        const int c = (int)(u - b * p.units_per_signal);
+        const int f_begin = c * p.chunk_frames;
+        const int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
+        Unit r;
+        r.x = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + (p.frame0 + f_begin) * (long long)p.hop;
+        r.out = p.out + b * p.out_batch_stride +
+                ((MODE == EPI_BAND) ? (long long)f_begin : (long long)f_begin * kout - p.kmin);
+        r.nf = f_end - f_begin;
+        return r;
+    };
+    // chunk j of a run of nf frames: j == 0 the first N + hop samples, then 2 hop per pair of frames,
+    // cut at the run's last sample (span = (nf - 1) hop + N).  Returns the sample count (0: none).
+    const int hop = p.hop;
+    auto chunk_lo = [&](int j) -> int { return j == 0 ? 0 : N + hop + 2 * hop * (j - 1); };
+    auto chunk_len = [&](int nf, int j) -> int {
+        const int span = (nf - 1) * hop + N;
+        const int lo = chunk_lo(j), hi = (j == 0) ? N + hop : lo + 2 * hop;
+        const int e = hi < span ? hi : span;
+        return e > lo ? e - lo : 0;
+    };
+    // lane 0: feed chunk j of the run into the ring (sample s of the run lives at s mod RS)
+    unsigned issued = 0, waited = 0;             // chunks issued / waited for: barrier = count & 1, parity = (count >> 1) & 1
+    auto issue = [&](const Unit& un, int j) {
+        const int len = chunk_len(un.nf, j);
+        if (len == 0) return;                    // (warp-uniform)
+        if (lane == 0) {
+            void* const bar = bars + (issued & 1u);
+            const int lo = chunk_lo(j);
+            const int pos = lo % RS;
+            const int first = (pos + len <= RS) ? len : RS - pos;
+            ring_expect(bar, (unsigned)(len * ESZ));
+            ring_copy(ring + (size_t)pos * ESZ, un.x + lo, (unsigned)(first * ESZ), bar);
+            if (first < len) ring_copy(ring, un.x + lo + first, (unsigned)((len - first) * ESZ), bar);
+        }
+        ++issued;
+    };
+    auto wait_chunk = [&](const Unit& un, int j) {
+        if (chunk_len(un.nf, j) == 0) return;
+#ifdef B2S_EMU
+        __syncwarp();
+#endif
+        ring_wait(bars + (waited & 1u), (waited >> 1) & 1u);
+        ++waited;
+    };
+
+    const long long ustride = (long long)gridDim.x * PP::FPC;
+    long long u_cur = dyn ? draw() : (long long)blockIdx.x * PP::FPC + warp;
+    long long u_next = 0;
+    Unit un{}, unn{};
+    if (u_cur < p.n_units) {
+        un = unit_of(u_cur);
+        issue(un, 0);
+        u_next = dyn ? draw() : u_cur + ustride;
+    }
+    while (u_cur < p.n_units) {
+        const bool have_next = u_next < p.n_units;
+        if (have_next) unn = unit_of(u_next);
+        const int nit = (un.nf + 1) >> 1;
+        int pos = 0;                                     // ring position (samples) of frame 2 it
+        for (int it = 0; it < nit; ++it) {
+            const int fr = 2 * it + h;                   // this half-warp's frame of the run
+            epi.act = fr < un.nf;
+            epi.row = un.out + (long long)fr * kout;
+            wait_chunk(un, it);
+
+            // ---- the frame's samples: slot i = x[4 (t + 16 i) .. + 3], 16 lanes read 256 contiguous bytes ----
+            int w0 = pos + h * hop;                      // frame start in the ring (samples)
+            if (w0 >= RS) w0 -= RS;
+            w0 = w0 / 4 + t;                             // in float4s of samples, this lane's first slot
+            const int RW4 = RS / 4;
+            auto slot_word = [&](int i) -> int {
+                int w = w0 + 16 * i;
+                return (w >= RW4) ? w - RW4 : w;
+            };
+            cpx2 v[16];
+            if constexpr (sizeof(Tin) == 8) {
+                // float64 samples: two trips over the staged samples instead of 128 live registers; the
+                // pivot is subtracted in double and the difference rounded once
+                double cd = 0.0;
+                if (p.detrend) {
+                    float s[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 q = RingLoad<double>::ld4(ring, slot_word(i));
+                        s[i] = (q.x + q.y) + (q.z + q.w);
+                        if ((i & 3) == 3) B2S_SCHED_FENCE();
+                    }
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; ++i) s[i] += s[i + w];
+                    float c = s[0];
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    cd = (double)(c * (1.0f / (float)N));
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 q = RingLoad<double>::ld4_minus(ring, slot_word(i), cd);
+                    v[i].re = cmk(q.x, q.y);
+                    v[i].im = cmk(q.z, q.w);
+                    if ((i & 3) == 3) B2S_SCHED_FENCE();
+                }
+            } else {
+                float4 raw[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) raw[i] = RingLoad<Tin>::ld4(ring, slot_word(i));
+                if (p.detrend) {
+                    // coarse mean (pivot): fixed tree over the lane's 64 samples, xor-butterfly over the 16 lanes
+                    float s[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s[i] = (raw[i].x + raw[i].y) + (raw[i].z + raw[i].w);
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                        for (int i = 0; i < w; ++i) s[i] += s[i + w];
+                    float c = s[0];
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    c *= 1.0f / (float)N;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i].re = pk_add(cmk(raw[i].x, raw[i].y), cmk(-c, -c));
+                        v[i].im = pk_add(cmk(raw[i].z, raw[i].w), cmk(-c, -c));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i].re = cmk(raw[i].x, raw[i].y);
+                        v[i].im = cmk(raw[i].z, raw[i].w);
+                    }
+                }
+            }
+            // every lane has read its samples: the ring positions before frame 2 (it + 1) are free
+            __syncwarp();
+            if (it + 1 < nit) issue(un, it + 1);
+            else if (have_next) issue(unn, 0);
+
+            if (p.detrend) {
+                // mean of the residual, removed inside the window multiply
+                float2 sr[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sr[i] = pk_add(v[i].re, v[i].im);
+#pragma unroll
+                for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                    for (int i = 0; i < w; ++i) sr[i] = pk_add(sr[i], sr[i + w]);
+                float r = sr[0].x + sr[0].y;
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                const float nr = r * (-1.0f / (float)N);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 w = sm4[PP::OFF_WIN + i * 16 + t];
+                    // (x' - r) w with ONE rounding: at this error level (rms 6e-6 of a bin 60 dB under the
+                    // peak) a second rounding per sample is measurable (7.7e-6, worst bin 1.09e-4 vs 0.82e-4)
+                    v[i].re = pk_fma(v[i].re, cmk(w.x, w.y), pk_muls(cmk(w.x, w.y), nr));
+                    v[i].im = pk_fma(v[i].im, cmk(w.z, w.w), pk_muls(cmk(w.z, w.w), nr));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float4 w = sm4[PP::OFF_WIN + i * 16 + t];
+                    v[i].re = pk_mul(v[i].re, cmk(w.x, w.y));
+                    v[i].im = pk_mul(v[i].im, cmk(w.z, w.w));
+                }
+            }
+
+            // ---- sub-transforms: radix-16, 16 x 16 transpose inside the half-warp, radix-16 ----
+            c2radix16(v);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cpx2 z = v[perm16(q)];
+                buf[ROW * t + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int tt = 0; tt < 16; ++tt) {
+                const float4 q4 = buf[ROW * tt + t];
+                v[tt] = cpx2{cmk(q4.x, q4.y), cmk(q4.z, q4.w)};
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = sm4[PP::OFF_TW1 + j * 16 + t];
+                if (j > 0) v[2 * j] = c2mul(v[2 * j], cmk(w.x, w.y));
+                v[2 * j + 1] = c2mul(v[2 * j + 1], cmk(w.z, w.w));
+            }
+            c2radix16(v);
+            __syncwarp();                        // every lane of the half-warp has consumed its reads
+
+            // ---- fused final stage.  v[perm16(pp)] = F[kap] = (F_A, F_B)[kap], kap = t + 16 pp, with
+            // F_A = X_0 + i X_2, F_B = X_1 + i X_3 (X_r the spectrum of x[4 m + r]).  Task pp < 8 takes the
+            // mirror F' = F[256 - kap] from lane 16 - t (its slot 15 - pp; lane 0 pairs kap = 16 pp with its own
+            // slot 16 - pp, and kap = 0 with itself) and produces bins kap, kap + 256, 256 - kap, 512 - kap.
+            auto task = [&](cpx2 F, cpx2 G, float2 w1, float2 w2, float2 w3, int kap, bool dc, bool mid) {
+                const cpx2 U{pk_add(F.re, G.re), pk_sub(F.im, G.im)};       // (2 X_0, 2 X_1) = F + conj(F')
+                const cpx2 V{pk_add(F.im, G.im), pk_sub(G.re, F.re)};       // (2 X_2, 2 X_3) = -i (F - conj(F'))
+                // Y_r = W_1024^(r kap) 2 X_r
+                const float y1r = fmaf(-U.im.y, w1.y, U.re.y * w1.x), y1i = fmaf(U.im.y, w1.x, U.re.y * w1.y);
+                const float y2r = fmaf(-V.im.x, w2.y, V.re.x * w2.x), y2i = fmaf(V.im.x, w2.x, V.re.x * w2.y);
+                const float y3r = fmaf(-V.im.y, w3.y, V.re.y * w3.x), y3i = fmaf(V.im.y, w3.x, V.re.y * w3.y);
+                const float2 ar = cmk(U.re.x, y1r), ai = cmk(U.im.x, y1i);  // (Y_0, Y_1)
+                const float2 br = cmk(y2r, y3r), bi = cmk(y2i, y3i);        // (Y_2, Y_3)
+                const float2 sr = pk_add(ar, br), si = pk_add(ai, bi);      // (Y_0 + Y_2, Y_1 + Y_3)
+                const float2 dr = pk_sub(ar, br), di = pk_sub(ai, bi);      // (Y_0 - Y_2, Y_1 - Y_3)
+                // 2 X[kap] = S0 + S1, 2 conj X[512 - kap] = S0 - S1, 2 X[kap + 256] = D0 - i D1, 2 conj X[256 - kap] = D0 + i D1
+                const float2 pr = cmk(sr.x + sr.y, sr.x - sr.y), pi = cmk(si.x + si.y, si.x - si.y);
+                const float2 qr = cmk(dr.x + di.y, dr.x - di.y), qi = cmk(di.x - dr.y, di.x + dr.y);
+                float2 ps = pk_fma(pr, pr, pk_mul(pi, pi));                 // bins kap, 512 - kap
+                const float2 pd = pk_fma(qr, qr, pk_mul(qi, qi));           // bins kap + 256, 256 - kap
+                if (dc) ps = pk_muls(ps, 0.5f);                             // DC / Nyquist carry scale, not 2 scale
+                epi.put(kap, ps.x);
+                epi.put(kap + M / 2, pd.x);
+                if (!mid) {
+                    epi.put(M - kap, ps.y);
+                    if (!dc) epi.put(M / 2 - kap, pd.y);
+                }
+            };
+            const float2* const w3tab = reinterpret_cast<const float2*>(sm4 + PP::OFF_W3);
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+                const cpx2 F = v[perm16(pp)];
+                const cpx2 s15 = v[perm16(15 - pp)], s16 = v[perm16((16 - pp) & 15)];
+                const float s0 = is0 ? s16.re.x : s15.re.x, s1 = is0 ? s16.re.y : s15.re.y;
+                const float s2 = is0 ? s16.im.x : s15.im.x, s3 = is0 ? s16.im.y : s15.im.y;
+                cpx2 G;
+                G.re = cmk(__shfl_sync(0xffffffffu, s0, partner), __shfl_sync(0xffffffffu, s1, partner));
+                G.im = cmk(__shfl_sync(0xffffffffu, s2, partner), __shfl_sync(0xffffffffu, s3, partner));
+                const float4 w12 = sm4[PP::OFF_W12 + pp * 16 + t];
+                const float2 w3 = w3tab[pp * 16 + t];
+                task(F, G, cmk(w12.x, w12.y), cmk(w12.z, w12.w), w3, t + 16 * pp, pp == 0 && is0, false);
+            }
+            if (is0) {                           // kap = 128 is its own mirror: bins 128 and 384
+                const cpx2 F = v[perm16(8)];
+                task(F, F, cmk(B2S_SQRT1_2, -B2S_SQRT1_2), cmk(0.f, -1.f), cmk(-B2S_SQRT1_2, -B2S_SQRT1_2), 128, false, true);
+            }
+            if constexpr (MODE == EPI_BAND) {
+                float bs = epi.band;
+                epi.band = 0.f;
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
+                if (is0 && epi.act) un.out[fr] = bs;
+            }
+            pos += 2 * hop;
+            while (pos >= RS) pos -= RS;
+        }
+        u_cur = u_next;
+        un = unn;
+        if (have_next) u_next = dyn ? draw() : u_next + ustride;
+    }
+    if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
+        __syncthreads();
+        if (tid == 0) {
+            const int done = atomicAdd(p.work + 1, 1);
+            if (done == (int)gridDim.x - 1) {
+                p.work[0] = 0;
+                p.work[1] = 0;
+            }
+        }
+    }
+}
+
+}  // namespace b2s

@@ -19,7 +19,7 @@ using namespace b2s;
 // which kernel family the last emu_stft_psd call ran (tests assert that a shape reaches the kernel it is meant for)
 static int g_last_family = 0;
 extern "C" int emu_last_family() { return g_last_family; }
-enum { FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
+enum { FAM_PAIR = 9, FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
 
 struct EmuLauncher {
     StftParams p;
@@ -28,8 +28,24 @@ struct EmuLauncher {
     bool duo1024 = true;
     bool allow_duo4 = true;
     bool allow_big = true;
+    bool allow_pair = true;
     bool dynamic_units = true;
     int work[2] = {0, 0};
+    const StftArgs* args = nullptr;
+    template <int LOG2N, typename Tin, int MODE>
+    int pair(const StftArgs& a) {
+        g_last_family = FAM_PAIR;
+        using PP = PairPlan<LOG2N>;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        q.ring = PP::ring_samples(a.hop);
+        if (pair_units >= 0) {
+            plan_pair_units(a, (long long)grid * PP::FPC, pair_units, dynamic_units, q);
+        }
+        emu::launch(grid, PP::NT, PP::smem_bytes(a.hop, (int)sizeof(Tin)), [&] { stft_psd_pair_kernel<LOG2N, Tin, MODE>(q); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
+    }
+    int pair_units = -1;         // >= 0: re-plan the runs with plan_pair_units (0: its default)
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs&) {
         g_last_family = FAM_DUO256;
@@ -134,6 +150,8 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (const char* v = getenv("B2S_DUO1024")) L.duo1024 = (atoi(v) != 0);
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
     if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_NO_PAIR")) L.allow_pair = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_PAIR_UNITS")) L.pair_units = atoi(v);
     if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     return dispatch_stft(a, L);
 }
