@@ -50,6 +50,15 @@ int b2s_version(void);
  * the reference: it has no device or collective layer) */
 int b2s_set_reserved_sms(int n);
 
+/* Diagnostic switches of the kernel selection.  Their defaults come from the
+ * B2S_* environment variables, read ONCE at the first call into the library (never on the per-call
+ * path); this entry changes one at run time: "no_duo", "duo1024", "no_duo4", "no_big", "no_pair",
+ * "static_units", "no_fused_sum", "sum_acc_smem" (value 0 / 1) and "pair_units" (work units per
+ * resident warp of the staged-sample kernel, 0 = default).  Not needed in normal use; the GPU tests
+ * use it to compare kernel variants bit for bit.  Returns B2S_OK or B2S_ERR_BAD_ARG.  (No
+ * counterpart in the reference.) */
+int b2s_set_option(const char* name, int value);
+
 /* One-shot all-reduce (sum) of `elems` floats over NVLink peer memory: every rank has written its
  * partial into a buffer that is mapped into all peers (peer_bufs[r] = the address of rank r's
  * partial in THIS process, e.g. from torch's symmetric-memory rendezvous), and owns a zero-

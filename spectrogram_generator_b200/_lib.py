@@ -91,6 +91,7 @@ _SUM_ARGS = [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_
 SIGNATURES = {
     "b2s_version": (c_int, []),
     "b2s_set_reserved_sms": (c_int, [c_int]),
+    "b2s_set_option": (c_int, [c_char_p, c_int]),
     "b2s_peer_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_longlong, c_void_p, c_float,
                                        c_void_p]),
     "b2s_last_error": (c_char_p, []),
@@ -126,6 +127,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def set_option(name: str, value: int):
+    """Diagnostic switch of the kernel selection (include/b2s.h: b2s_set_option)."""
+    check(load().b2s_set_option(name.encode(), int(value)), "b2s_set_option")
 
 
 def check(rc: int, what: str):

@@ -140,10 +140,11 @@ struct EnvSwitches {
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
     }
 };
-const EnvSwitches& env() {
-    static const EnvSwitches e;
+EnvSwitches& env_mut() {
+    static EnvSwitches e;        // the B2S_* environment is read once, at the first call
     return e;
 }
+const EnvSwitches& env() { return env_mut(); }
 
 // One launch of an STFT kernel (either family): persistent grid sized from the
 // occupancy, work units sized from the grid (b2s::plan_stft).
@@ -421,6 +422,24 @@ int b2s_set_reserved_sms(int n) {
 }
 
 const char* b2s_last_error(void) { return g_err.c_str(); }
+
+int b2s_set_option(const char* name, int value) {
+    if (!name) return fail(B2S_ERR_BAD_ARG, "b2s_set_option: null name");
+    EnvSwitches& e = env_mut();
+    const std::string n(name);
+    const bool on = value != 0;
+    if (n == "no_duo") e.allow_duo = !on;
+    else if (n == "duo1024") e.duo1024 = on;
+    else if (n == "no_duo4") e.allow_duo4 = !on;
+    else if (n == "no_big") e.allow_big = !on;
+    else if (n == "static_units") e.dynamic_units = !on;
+    else if (n == "no_pair") e.allow_pair = !on;
+    else if (n == "no_fused_sum") e.fused_sum = !on;
+    else if (n == "sum_acc_smem") e.sum_acc_smem = on;
+    else if (n == "pair_units") e.pair_units = value;
+    else return fail(B2S_ERR_BAD_ARG, "b2s_set_option: unknown option " + n);
+    return B2S_OK;
+}
 
 int b2s_nperseg_support(int nperseg) { return b2s::nperseg_support(nperseg); }
 

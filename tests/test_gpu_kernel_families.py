@@ -73,6 +73,64 @@ def test_family(nperseg, hop):
     np.testing.assert_allclose(band, full[:, :, k0:k1 + 1].astype(np.float64).sum(axis=-1), rtol=3e-6)
 
 
+@pytest.mark.parametrize("hop", [256, 128, 512, 896, 1024, 36, 300, 768])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_staged_sample_pair_kernel(hop, detrend):
+    """nperseg 1024 on 16-byte aligned rows: the staged-sample pair kernel (b2s_pair_kernel.cuh -- TMA
+    bulk copies into a per-warp ring, any hop that is a multiple of 4).  Parity with the oracle, and
+    bit-identity across run lengths (rings wrap at different places), the static schedule, float64
+    samples, frame ranges / crops, with the four-step duo kernel as a second opinion."""
+    from spectrogram_generator_b200 import _lib
+    rng = np.random.default_rng(hop)
+    B, nfr = 3, 23
+    n = (1024 + hop * (nfr - 1) + 5 + 3) // 4 * 4
+    x = _signal(rng, B, n, dc=-70.0 if detrend else 0.0)
+    kw = dict(window=("tukey", .25), nperseg=1024, noverlap=1024 - hop, detrend=detrend)
+    plan = sg.triage(n, 20000.0, kw["window"], 1024, 1024 - hop, None, detrend, True, "density", "psd")
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    full = eng.stft_psd(xd, plan)
+    assert_parity(full.cpu().numpy(), So, what=f"pair 1024/{hop}")
+    try:
+        for units in (1, 3, 50):                   # runs of 23, 8 and 4 frames per warp
+            _lib.set_option("pair_units", units)
+            assert torch.equal(eng.stft_psd(xd, plan), full)
+        _lib.set_option("static_units", 1)
+        assert torch.equal(eng.stft_psd(xd, plan), full)
+    finally:
+        _lib.set_option("pair_units", 0)
+        _lib.set_option("static_units", 0)
+    assert torch.equal(eng.stft_psd(xd.double(), plan), full)
+    part = eng.stft_psd(xd, plan, kmin=7, kmax=400, frame0=3, nframes=nfr - 5)
+    assert torch.equal(part, full[:, 3:nfr - 2, 7:401])
+    band = eng.band_power(xd, plan, 7, 400).cpu().numpy()
+    np.testing.assert_allclose(band, full[:, :, 7:401].double().sum(dim=-1).cpu().numpy(), rtol=3e-6)
+    _lib.set_option("no_pair", 1)
+    try:
+        other = eng.stft_psd(xd, plan)
+    finally:
+        _lib.set_option("no_pair", 0)
+    assert not torch.equal(other, full)            # a different kernel did run
+    assert_parity(other.cpu().numpy(), So, what=f"duo 1024/{hop}")
+
+
+def test_float64_samples_on_a_large_dc_level_keep_their_signal():
+    """float64 input (neo / NIX sweeps, SweepManager.py:135-136): the pair kernel subtracts the frame's
+    pivot in double before the cast, so a 1e-3 signal on a DC level of 1e4 -- which float32 samples
+    cannot even represent -- comes out within the bar."""
+    rng = np.random.default_rng(3)
+    n = 1024 + 896 * 20
+    t = np.arange(n)
+    x = 1e4 + 1e-3 * (np.sin(2 * np.pi * 0.05 * t) + 0.1 * rng.standard_normal(n))
+    f, tt, So = stft_oracle.spectrogram(x, fs=1000.0, nperseg=1024)
+    plan = sg.triage(n, 1000.0, ("tukey", .25), 1024, None, None, "constant", True, "density", "psd")
+    S = sg.engine().stft_psd(torch.from_numpy(x.reshape(1, -1)).cuda(), plan)[0].cpu().numpy()
+    assert_parity(S.T, So, what="float64 samples, DC 1e4")
+
+
 @pytest.mark.parametrize("nperseg,hop", [(512, 128), (256, 64), (1024, 256), (2048, 512), (1024, 896)])
 def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg, hop):
     """Enough work for the atomic work counter (b2s_api.cu: launch_any_impl): two launches give the
@@ -131,13 +189,18 @@ def test_fused_sum_matches_the_two_pass_sum_and_the_public_mean(monkeypatch):
     xd = torch.from_numpy(x).cuda()
     S, tot = eng.stft_psd_sum(xd, plan)
     # running sums in shared memory instead of tensor memory: the same additions in the same order
-    monkeypatch.setenv("B2S_SUM_ACC_SMEM", "1")
-    S1, tot1 = eng.stft_psd_sum(xd, plan)
-    monkeypatch.delenv("B2S_SUM_ACC_SMEM")
+    from spectrogram_generator_b200 import _lib
+    _lib.set_option("sum_acc_smem", 1)
+    try:
+        S1, tot1 = eng.stft_psd_sum(xd, plan)
+    finally:
+        _lib.set_option("sum_acc_smem", 0)
     assert torch.equal(S1, S) and torch.equal(tot1, tot)
-    monkeypatch.setenv("B2S_NO_FUSED_SUM", "1")
-    S0, tot0 = eng.stft_psd_sum(xd, plan)
-    monkeypatch.delenv("B2S_NO_FUSED_SUM")
+    _lib.set_option("no_fused_sum", 1)
+    try:
+        S0, tot0 = eng.stft_psd_sum(xd, plan)
+    finally:
+        _lib.set_option("no_fused_sum", 0)
     assert torch.equal(S, S0)
     torch.testing.assert_close(tot, tot0, rtol=2e-6, atol=0)
     assert torch.equal(tot0, eng.batch_sum(eng.stft_psd(xd, plan)))
