@@ -126,6 +126,7 @@ struct EnvSwitches {
     bool allow_duo = true, duo1024 = true, allow_duo4 = true, allow_big = true, dynamic_units = true;
     bool allow_pair = true, fused_sum = true, sum_acc_smem = false;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
+    int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
     EnvSwitches() {
         auto on = [](const char* name) { const char* v = getenv(name); return v && atoi(v) != 0; };
         auto off0 = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) != 0 : dflt; };
@@ -138,6 +139,7 @@ struct EnvSwitches {
         fused_sum = !on("B2S_NO_FUSED_SUM");
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
+        if (const char* v = getenv("B2S_PAIR_NT")) pair_nt = atoi(v);
     }
 };
 EnvSwitches& env_mut() {
@@ -204,35 +206,49 @@ struct PairState {
 };
 std::map<std::pair<const void*, long long>, PairState> g_pair;     // (kernel, device << 32 | smem) -> residency
 
-int launch_pair_impl(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
+int launch_pair_impl(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
+                     bool dynamic) {
     using PP = b2s::PairPlan<10>;
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-    const size_t smem = PP::smem_bytes(a.hop, esz);
+    // CTA shape: 128 threads (several CTAs per SM, 168 registers) or one wide CTA per SM (136 registers,
+    // as many warps as its shared memory allows); B2S_PAIR_NT / b2s_set_option("pair_nt") overrides
+    // Measured on B200 (tools/microbench.py --set n1024x, profiles/r2_pair_cta_width.md): one wide CTA per SM
+    // (the constant tables once per SM, up to 15 warps at 128 registers) wins from hop 512 down and with
+    // little overlap, where three 128-thread CTAs no longer fit their rings (hop 1024: 0.70 -> 0.81 of the HBM peak).
+    int nt = (a.hop > 768) ? 384 : 480;
+    if (a.batch * a.nframes < 64 * di.sm_count) nt = PP::NT;      // small launches: more, smaller CTAs
+    if (env().pair_nt > 0) nt = env().pair_nt / 32 * 32;
+    if (nt < 32) nt = 32;
+    if (nt > PP::NT_WIDE) nt = PP::NT_WIDE;
+    while (nt > PP::NT && (int)PP::smem_bytes(a.hop, esz, nt) > di.smem_optin) nt -= 32;
+    if (nt > PP::NT) kern = kern_wide;
+    const size_t smem = PP::smem_bytes(a.hop, esz, nt);
     if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this hop");
     int occ = 0;
     {
         std::lock_guard<std::mutex> g(g_mu);
-        PairState& ks = g_pair[std::make_pair(kern, ((long long)dev << 32) | (long long)smem)];
+        PairState& ks = g_pair[std::make_pair(kern, ((long long)dev << 40) | ((long long)nt << 24) | (long long)smem)];
         if (ks.occ == 0) {
             // the attribute is the maximum any launch of this kernel may ask for
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, PP::NT, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, kern, nt, smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
             if (ks.occ < 1) ks.occ = 1;
         }
         occ = ks.occ;
     }
+    const int fpc = nt / 32;                 // runs in flight per CTA: one per warp
     const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
     const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
-    const long long resident_warps = resident_ctas * PP::FPC;
+    const long long resident_warps = resident_ctas * fpc;
     b2s::StftParams p{};
     std::string err;
     dynamic = dynamic && (a.batch * a.nframes >= 16 * resident_warps) && !stream_capturing(stream);
-    rc = b2s::plan_stft(a, PP::FPC, resident_warps, p, err, dynamic);
+    rc = b2s::plan_stft(a, fpc, resident_warps, p, err, dynamic);
     if (rc < 0) return fail(rc, err);
     if (p.n_units == 0) return B2S_OK;
     b2s::plan_pair_units(a, resident_warps, env().pair_units, dynamic, p);
@@ -243,10 +259,10 @@ int launch_pair_impl(const void* kern, int esz, const b2s::StftArgs& a, cudaStre
     }
     rc = twiddles(dev, a.nperseg, false, &p.tw);
     if (rc != B2S_OK) return rc;
-    const long long need = (p.n_units + PP::FPC - 1) / PP::FPC;
+    const long long need = (p.n_units + fpc - 1) / fpc;
     const long long grid = (need < resident_ctas) ? need : resident_ctas;
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)PP::NT), args, smem, stream);
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)nt), args, smem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "pair stft kernel launch");
     return B2S_OK;
 }
@@ -407,8 +423,9 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
     return launch_any_impl(kern, nt, smem, fpc, a, stream, false, dynamic);
 }
 
-int b2s_launch_pair(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
-    return launch_pair_impl(kern, esz, a, stream, dynamic);
+int b2s_launch_pair(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
+                    bool dynamic) {
+    return launch_pair_impl(kern, kern_wide, esz, a, stream, dynamic);
 }
 
 extern "C" {
@@ -437,6 +454,7 @@ int b2s_set_option(const char* name, int value) {
     else if (n == "no_fused_sum") e.fused_sum = !on;
     else if (n == "sum_acc_smem") e.sum_acc_smem = on;
     else if (n == "pair_units") e.pair_units = value;
+    else if (n == "pair_nt") e.pair_nt = value;
     else return fail(B2S_ERR_BAD_ARG, "b2s_set_option: unknown option " + n);
     return B2S_OK;
 }

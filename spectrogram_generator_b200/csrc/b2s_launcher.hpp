@@ -14,7 +14,8 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
                    bool dynamic = false);
 
 // One launch of the staged-sample pair kernel (b2s_pair_kernel.cuh).  Defined in b2s_api.cu.
-int b2s_launch_pair(const void* kern, int esz, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic);
+int b2s_launch_pair(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
+                    bool dynamic);
 
 namespace b2s {
 
@@ -27,8 +28,9 @@ struct CudaLauncher {
     bool allow_pair = true;
     template <int LOG2N, typename Tin, int MODE>
     int pair(const StftArgs& a) {
-        return b2s_launch_pair((const void*)stft_psd_pair_kernel<LOG2N, Tin, MODE>, (int)sizeof(Tin), a, stream,
-                               dynamic_units);
+        return b2s_launch_pair((const void*)stft_psd_pair_kernel<LOG2N, Tin, MODE>,
+                               (const void*)stft_psd_pair_wide_kernel<LOG2N, Tin, MODE>,
+                               (int)sizeof(Tin), a, stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int big(const StftArgs& a) {

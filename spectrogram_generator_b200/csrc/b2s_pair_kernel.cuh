@@ -45,23 +45,24 @@ struct PairPlan {
     static constexpr int N = PL::N, M = PL::M;
     static constexpr int R = M / 256;
     static_assert(R == 2, "pair kernel: nperseg 1024 (four real sub-sequences of 256 points)");
-    static constexpr int NT = 128;                       // threads per CTA
-    static constexpr int NW = NT / 32;                   // warps = rings per CTA
-    static constexpr int NHW = NT / 16;                  // frames in flight per CTA
-    static constexpr int FPC = NW;                       // work units in flight per CTA (one run per warp)
+    // CTA shapes: 128 threads x 3 CTAs per SM (<= 168 registers), or ONE CTA of up to 480 threads per SM
+    // (<= 136 registers): nothing in the main loop is CTA-wide, so the CTA is only the unit that shares
+    // the constant tables.  `nt` below is the launch's block size.
+    static constexpr int NT = 128;
+    static constexpr int NT_WIDE = 512;
     static constexpr int ROW = 17, BUF = 16 * ROW;       // transpose buffer of one frame, float4 units
     // shared memory, float4 units
     static constexpr int OFF_WIN = 0;                    // [16][16] taps of slot i, lane t: w[4 (t + 16 i) .. + 3] * sqrt(scale/2)
     static constexpr int OFF_TW1 = OFF_WIN + 16 * 16;    // [8][16] W_256^(t' q), t' = 2j, 2j+1
     static constexpr int OFF_W12 = OFF_TW1 + 8 * 16;     // [8][16] (W_1024^kap, W_1024^(2 kap)), kap = t + 16 pp
     static constexpr int OFF_W3 = OFF_W12 + 8 * 16;      // [8][16] float2 W_1024^(3 kap)  (half a float4 each)
-    static constexpr int OFF_BUF = OFF_W3 + 4 * 16;
-    static constexpr int OFF_BAR = OFF_BUF + NHW * BUF;  // NW x 2 mbarriers (one float4 per warp)
-    static constexpr int OFF_RING = OFF_BAR + NW;        // NW rings of ring_samples elements each
+    static constexpr int OFF_BUF = OFF_W3 + 4 * 16;      // nt/16 transpose buffers
+    B2S_HD static int off_bar(int nt) { return OFF_BUF + (nt / 16) * BUF; }   // nt/32 x 2 mbarriers (one float4 per warp)
+    B2S_HD static int off_ring(int nt) { return off_bar(nt) + nt / 32; }     // nt/32 rings of ring_samples elements each
     // ring: the N + hop samples of a pair of frames, rounded up to 128 bytes
     static int ring_samples(int hop) { return (N + hop + 31) / 32 * 32; }
-    static size_t smem_bytes(int hop, int esz) {
-        return (size_t)OFF_RING * sizeof(float4) + (size_t)NW * ring_samples(hop) * esz;
+    static size_t smem_bytes(int hop, int esz, int nt = NT) {
+        return (size_t)off_ring(nt) * sizeof(float4) + (size_t)(nt / 32) * ring_samples(hop) * esz;
     }
 };
 
@@ -70,16 +71,18 @@ inline bool pair_kernel_ok(const void* x, int x_is_f64, long long batch, long lo
                            long long frame0) {
     (void)frame0;
     if (nperseg != 1024) return false;
-    const int per16 = x_is_f64 ? 2 : 4;                  // samples per 16 bytes
+    (void)x_is_f64;              // the same rule for float and double rows: both take the same kernel
     if (reinterpret_cast<uintptr_t>(x) % 16) return false;
     if (hop % 4 || hop < 32 || hop > nperseg) return false;
-    if (batch > 1 && (x_batch_stride % per16)) return false;
+    if (batch > 1 && (x_batch_stride % 4)) return false;
     return true;
 }
 
 #ifdef B2S_EMU
+#define B2S_MAXNREG(n)
 #define B2S_SCHED_FENCE() do {} while (0)
 #else
+#define B2S_MAXNREG(n) __maxnreg__(n)
 // keeps the compiler from hoisting every load of an unrolled loop above their uses (register pressure)
 #define B2S_SCHED_FENCE() asm volatile("" ::: "memory")
 #endif
@@ -160,8 +163,23 @@ struct EpiOne {
     }
 };
 
-template <int LOG2N, typename Tin, int MODE, int MINB = 3>
-B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, MINB) stft_psd_pair_kernel(const StftParams p) {
+template <int LOG2N, typename Tin, int MODE, int MINB>
+B2S_DEVICE void stft_psd_pair_body(const StftParams& p);
+
+// 128 threads x 3 CTAs per SM
+template <int LOG2N, typename Tin, int MODE>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, 3) stft_psd_pair_kernel(const StftParams p) {
+    stft_psd_pair_body<LOG2N, Tin, MODE, 3>(p);
+}
+// one CTA of up to 512 threads per SM: 128 registers (registers are handed out to four warps at a time,
+// so 15 warps of 136 do not fit)
+template <int LOG2N, typename Tin, int MODE>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(512, 1) stft_psd_pair_wide_kernel(const StftParams p) {
+    stft_psd_pair_body<LOG2N, Tin, MODE, 1>(p);
+}
+
+template <int LOG2N, typename Tin, int MODE, int MINB>
+B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
     using PL = Plan<LOG2N>;
     using PP = PairPlan<LOG2N>;
     constexpr int N = PP::N, M = PP::M, ROW = PP::ROW;
@@ -174,20 +192,22 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, MINB) stft_psd_pair_kerne
     const int h = lane >> 4;                             // frame of the pair this half-warp owns
     const int t = lane & 15;
     float4* const buf = sm4 + PP::OFF_BUF + (tid >> 4) * PP::BUF;
-    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::OFF_BAR + warp);
+    const int nt = (int)blockDim.x;
+    const int nwarps = nt >> 5;
+    unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::off_bar(nt) + warp);
     const int RS = p.ring;                               // ring length in samples
-    unsigned char* const ring = reinterpret_cast<unsigned char*>(sm4 + PP::OFF_RING) + (size_t)warp * RS * ESZ;
+    unsigned char* const ring = reinterpret_cast<unsigned char*>(sm4 + PP::off_ring(nt)) + (size_t)warp * RS * ESZ;
 
     // ---- constant tables, once per CTA; the PSD scale goes into the window ----
     {
         const float csc = sqrtf(0.5f * p.scale);
         const float4* w4 = reinterpret_cast<const float4*>(p.window);
-        for (int i = tid; i < 16 * 16; i += PP::NT) {
+        for (int i = tid; i < 16 * 16; i += nt) {
             const float4 w = __ldg(w4 + i);             // taps of samples 4 (t + 16 i) .. + 3, i * 16 + t == i
             sm4[PP::OFF_WIN + i] = make_float4(w.x * csc, w.y * csc, w.z * csc, w.w * csc);
         }
         float2* const w3tab = reinterpret_cast<float2*>(sm4 + PP::OFF_W3);
-        for (int i = tid; i < 8 * 16; i += PP::NT) {
+        for (int i = tid; i < 8 * 16; i += nt) {
             const int j = i >> 4, l = i & 15;
             const float2 ta = (j == 0) ? cmk(1.f, 0.f) : __ldg(p.tw + PL::OFF_P1 + (2 * j - 1) * 16 + l);
             const float2 tb = __ldg(p.tw + PL::OFF_P1 + (2 * j) * 16 + l);
@@ -274,8 +294,8 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, MINB) stft_psd_pair_kerne
         ++waited;
     };
 
-    const long long ustride = (long long)gridDim.x * PP::FPC;
-    long long u_cur = dyn ? draw() : (long long)blockIdx.x * PP::FPC + warp;
+    const long long ustride = (long long)gridDim.x * nwarps;
+    long long u_cur = dyn ? draw() : (long long)blockIdx.x * nwarps + warp;
     long long u_next = 0;
     Unit un{}, unn{};
     if (u_cur < p.n_units) {

@@ -40,7 +40,7 @@ struct EmuLauncher {
         if (dynamic_units) q.work = work;
         q.ring = PP::ring_samples(a.hop);
         if (pair_units >= 0) {
-            plan_pair_units(a, (long long)grid * PP::FPC, pair_units, dynamic_units, q);
+            plan_pair_units(a, (long long)grid * (PP::NT / 32), pair_units, dynamic_units, q);
         }
         emu::launch(grid, PP::NT, PP::smem_bytes(a.hop, (int)sizeof(Tin)), [&] { stft_psd_pair_kernel<LOG2N, Tin, MODE>(q); });
         return (work[0] == 0 && work[1] == 0) ? 0 : -100;
