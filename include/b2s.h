@@ -38,6 +38,7 @@ extern "C" {
 #define B2S_ERR_BAD_ARG (-1)     /* invalid argument (mirrors SciPy's ValueError cases) */
 #define B2S_ERR_UNSUPPORTED (-2) /* nperseg not handled by this entry */
 #define B2S_ERR_CUDA (-3)        /* CUDA runtime error; see b2s_last_error() */
+#define B2S_ERR_TIMEOUT (-4)     /* b2s_peer_allreduce_status: a peer missed the all-reduce's time-out */
 
 #define B2S_OUT_LINEAR 0 /* PSD / power spectrum, linear */
 #define B2S_OUT_DB 1     /* 10*log10(max(S, db_floor)) */
@@ -59,6 +60,10 @@ int b2s_set_reserved_sms(int n);
  * counterpart in the reference.) */
 int b2s_set_option(const char* name, int value);
 
+/* Name of the STFT kernel family the calling thread launched last ("none" before the first launch),
+ * with nperseg / hop / sample type -- what bench.py prints next to each measured shape. */
+const char* b2s_last_kernel(void);
+
 /* One-shot all-reduce (sum) of `elems` floats over NVLink peer memory: every rank has written its
  * partial into a buffer that is mapped into all peers (peer_bufs[r] = the address of rank r's
  * partial in THIS process, e.g. from torch's symmetric-memory rendezvous), and owns a zero-
@@ -70,6 +75,13 @@ int b2s_set_option(const char* name, int value);
 int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
                            int rank, unsigned int epoch, long long elems, float* out, float post_scale,
                            void* stream);
+
+/* The all-reduce waits for a late peer for B2S_PEER_TIMEOUT_MS (default 120 000) of wall-clock time
+ * (%globaltimer), polling with a nanosleep back-off; every rank must therefore enqueue its call
+ * within that window.  A kernel whose wait expires does NOT trap: it leaves `out` unwritten and
+ * raises a per-device flag.  This entry synchronises `stream`, reads the flag and clears it:
+ * B2S_OK, or B2S_ERR_TIMEOUT with the missing rank in b2s_last_error(). */
+int b2s_peer_allreduce_status(void* stream);
 const char* b2s_last_error(void);
 
 /* 1 if `nperseg` runs on the fused radix-16 Stockham kernels (powers of two in

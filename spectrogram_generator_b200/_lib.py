@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libb200stft.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(_ROOT, "include", "b2s.h")
 
-B2S_OK, B2S_ERR_BAD_ARG, B2S_ERR_UNSUPPORTED, B2S_ERR_CUDA = 0, -1, -2, -3
+B2S_OK, B2S_ERR_BAD_ARG, B2S_ERR_UNSUPPORTED, B2S_ERR_CUDA, B2S_ERR_TIMEOUT = 0, -1, -2, -3, -4
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -94,7 +94,9 @@ SIGNATURES = {
     "b2s_set_option": (c_int, [c_char_p, c_int]),
     "b2s_peer_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_longlong, c_void_p, c_float,
                                        c_void_p]),
+    "b2s_peer_allreduce_status": (c_int, [c_void_p]),
     "b2s_last_error": (c_char_p, []),
+    "b2s_last_kernel": (c_char_p, []),
     "b2s_nperseg_support": (c_int, [c_int]),
     "b2s_frame_count": (c_longlong, [c_longlong, c_int, c_int]),
     "b2s_stft_psd_f32": (c_int, _STFT_ARGS),
@@ -134,6 +136,10 @@ def set_option(name: str, value: int):
     check(load().b2s_set_option(name.encode(), int(value)), "b2s_set_option")
 
 
+def last_kernel() -> str:
+    return load().b2s_last_kernel().decode("utf-8", "replace")
+
+
 def check(rc: int, what: str):
     if rc == B2S_OK:
         return
@@ -142,4 +148,6 @@ def check(rc: int, what: str):
         raise ValueError(f"{what}: {msg}")
     if rc == B2S_ERR_UNSUPPORTED:
         raise NotImplementedError(f"{what}: {msg}")
+    if rc == B2S_ERR_TIMEOUT:
+        raise TimeoutError(f"{what}: {msg}")
     raise B2SError(f"{what}: {msg} (code {rc})")

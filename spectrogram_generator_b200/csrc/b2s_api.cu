@@ -19,6 +19,7 @@
 namespace {
 
 thread_local std::string g_err;
+thread_local std::string g_last_kernel = "none";
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -80,6 +81,26 @@ int twiddles(int dev, int nperseg, bool dft, const float2** out) {
     return B2S_OK;
 }
 
+// error flag of the peer all-reduce (set by the kernel when a peer misses the time-out), one per device
+std::map<int, int*> g_peer_err;     // guarded by g_mu
+int peer_err_flag(int dev, int** out) {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_peer_err.find(dev);
+    if (it == g_peer_err.end()) {
+        int* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, 32 * sizeof(int));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(peer error flag)");
+        e = cudaMemset(d, 0, 32 * sizeof(int));
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return cuda_fail(e, "cudaMemset(peer error flag)");
+        }
+        it = g_peer_err.emplace(dev, d).first;
+    }
+    *out = it->second;
+    return B2S_OK;
+}
+
 struct KernelState {
     int occ = 0;
     int dev = -1;
@@ -127,6 +148,7 @@ struct EnvSwitches {
     bool allow_pair = true, fused_sum = true, sum_acc_smem = false;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
     int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
+    int peer_timeout_ms = 0;     // B2S_PEER_TIMEOUT_MS: how long the peer all-reduce waits for a late rank (0: 120 s)
     EnvSwitches() {
         auto on = [](const char* name) { const char* v = getenv(name); return v && atoi(v) != 0; };
         auto off0 = [](const char* name, bool dflt) { const char* v = getenv(name); return v ? atoi(v) != 0 : dflt; };
@@ -140,6 +162,7 @@ struct EnvSwitches {
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
         if (const char* v = getenv("B2S_PAIR_NT")) pair_nt = atoi(v);
+        if (const char* v = getenv("B2S_PEER_TIMEOUT_MS")) peer_timeout_ms = atoi(v);
     }
 };
 EnvSwitches& env_mut() {
@@ -313,7 +336,10 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
         int rc = b2s::validate_args(a, err);
         if (rc < 0) return fail(rc, err);
     }
-    if (b2s::nperseg_support(nperseg) == 2) return launch_dft<Tin>(a, (cudaStream_t)stream);
+    if (b2s::nperseg_support(nperseg) == 2) {
+        b2s_note_kernel("dft_psd_kernel (direct DFT)", a);
+        return launch_dft<Tin>(a, (cudaStream_t)stream);
+    }
     b2s::CudaLauncher L{(cudaStream_t)stream};
     const EnvSwitches& sw = env();
     L.allow_duo = sw.allow_duo;
@@ -408,7 +434,10 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     const long long elems = nframes * (nperseg / 2 + 1);
     int slots = (!env().fused_sum || !env().allow_duo || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
     if (slots > 8) slots = 0;           // hop 448 / 512: per-sweep frame-duo kernel, no sum-fused variant
-    if (slots) return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
+    if (slots) {
+        b2s_note_kernel("stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
+        return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
+    }
     // every other shape: the per-sweep kernel of its family, then the two-pass sum
     int rc = stft_entry<Tin>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR, 0.f, 0,
                              nperseg / 2, frame0, nframes, out, out_batch_stride, stream);
@@ -417,6 +446,11 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
 }
 
 }  // namespace
+
+void b2s_note_kernel(const char* family, const b2s::StftArgs& a) {
+    g_last_kernel = std::string(family) + " nperseg " + std::to_string(a.nperseg) + " hop " + std::to_string(a.hop) +
+                    (a.x_is_f64 ? " f64" : " f32");
+}
 
 int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::StftArgs& a, cudaStream_t stream,
                    bool dynamic) {
@@ -440,6 +474,8 @@ int b2s_set_reserved_sms(int n) {
 
 const char* b2s_last_error(void) { return g_err.c_str(); }
 
+const char* b2s_last_kernel(void) { return g_last_kernel.c_str(); }
+
 int b2s_set_option(const char* name, int value) {
     if (!name) return fail(B2S_ERR_BAD_ARG, "b2s_set_option: null name");
     EnvSwitches& e = env_mut();
@@ -455,6 +491,7 @@ int b2s_set_option(const char* name, int value) {
     else if (n == "sum_acc_smem") e.sum_acc_smem = on;
     else if (n == "pair_units") e.pair_units = value;
     else if (n == "pair_nt") e.pair_nt = value;
+    else if (n == "peer_timeout_ms") e.peer_timeout_ms = value;
     else return fail(B2S_ERR_BAD_ARG, "b2s_set_option: unknown option " + n);
     return B2S_OK;
 }
@@ -577,11 +614,34 @@ int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned l
     const int reserve = g_reserved_sms.load();
     const long long cap = (reserve > 0 && reserve < di.sm_count) ? 3LL * reserve : di.sm_count;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
+    int* err_flag = nullptr;
+    rc = peer_err_flag(dev, &err_flag);
+    if (rc != B2S_OK) return rc;
+    const unsigned long long timeout_ns = (unsigned long long)(env().peer_timeout_ms > 0 ? env().peer_timeout_ms : 120000) * 1000000ULL;
     b2s::peer_allreduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out, post_scale,
-                                                                         vec_ok);
+                                                                         vec_ok, timeout_ns, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce_kernel launch");
     return B2S_OK;
+}
+
+int b2s_peer_allreduce_status(void* stream) {
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    int* err_flag = nullptr;
+    rc = peer_err_flag(dev, &err_flag);
+    if (rc != B2S_OK) return rc;
+    int host = 0;
+    cudaError_t e = cudaMemcpyAsync(&host, err_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "b2s_peer_allreduce_status");
+    if (host == 0) return B2S_OK;
+    cudaMemsetAsync(err_flag, 0, sizeof(int), (cudaStream_t)stream);
+    return fail(B2S_ERR_TIMEOUT, "b2s_peer_allreduce_f32: rank " + std::to_string(host - 1) +
+                                     " did not announce its partial within the time-out (B2S_PEER_TIMEOUT_MS); the result "
+                                     "of that reduce was not written");
 }
 
 int b2s_display_scale_f32(const float* s, long long elems, int log_scale, float global_max, float* out,

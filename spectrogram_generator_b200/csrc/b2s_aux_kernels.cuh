@@ -53,23 +53,45 @@ struct PeerPtrs {
     unsigned* pad[16];          // every rank's signal pad, at the slot block of this epoch's parity
 };
 
+// Waiting for a peer is bounded by WALL-CLOCK time (%globaltimer against `timeout_ns`, minutes by
+// default: a rank that is legitimately late -- still loading sweeps, first-call allocations, a
+// debugger pause -- must not take the job down), polls back off with nanosleep so that the few
+// waiting CTAs leave the issue slots of their SMs to the STFT CTAs they share them with, and on
+// expiry the kernel sets `*err_flag` (checked by b2s_peer_allreduce_status) and returns without
+// writing `out` instead of trapping (a trap poisons the CUDA context of every waiting rank).
+B2S_DEVICE unsigned long long b2s_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 B2S_GLOBAL void peer_allreduce_kernel(const PeerPtrs pp, int world, int rank, unsigned epoch, long long elems,
-                                      float* __restrict__ out, float post_scale, int vec_ok) {
+                                      float* __restrict__ out, float post_scale, int vec_ok,
+                                      unsigned long long timeout_ns, int* err_flag) {
     if (blockIdx.x == 0 && (int)threadIdx.x < world) {
         __threadfence_system();
         unsigned* dst = pp.pad[threadIdx.x] + rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
     }
+    int late = 0;
     if ((int)threadIdx.x < world) {
         const unsigned* src = pp.pad[rank] + threadIdx.x;
         unsigned v;
-        long long spins = 0;
-        do {
+        unsigned ns = 32;
+        const unsigned long long t0 = b2s_globaltimer_ns();
+        for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
-            if (++spins > (1LL << 26)) __trap();          // a peer never arrived (~1 min): fail loudly instead of hanging
-        } while ((int)(v - epoch) < 0);
+            if ((int)(v - epoch) >= 0) break;
+            if (b2s_globaltimer_ns() - t0 > timeout_ns) {      // a peer never arrived within the window
+                late = 1;
+                atomicExch(err_flag, (int)(threadIdx.x + 1));     // which rank was missing
+                break;
+            }
+            __nanosleep(ns);
+            if (ns < 1024) ns *= 2;
+        }
     }
-    __syncthreads();
+    if (__syncthreads_or(late)) return;
     // peer memory is read with ld.cv (never from a stale L1 line), 16 bytes at a time when the
     // buffers allow it, all ranks' loads in flight before the adds; the adds go in rank order
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -17,6 +17,9 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
 int b2s_launch_pair(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
                     bool dynamic);
 
+// Records which kernel the calling thread launched last (b2s_last_kernel() in include/b2s.h).
+void b2s_note_kernel(const char* family, const b2s::StftArgs& a);
+
 namespace b2s {
 
 struct CudaLauncher {
@@ -28,12 +31,14 @@ struct CudaLauncher {
     bool allow_pair = true;
     template <int LOG2N, typename Tin, int MODE>
     int pair(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_pair_kernel (staged samples: TMA ring, sub-sequence pairs in fp32x2)", a);
         return b2s_launch_pair((const void*)stft_psd_pair_kernel<LOG2N, Tin, MODE>,
                                (const void*)stft_psd_pair_wide_kernel<LOG2N, Tin, MODE>,
                                (int)sizeof(Tin), a, stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int big(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_big_kernel (three passes, one frame per CTA)", a);
         using BP = BigPlan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_big_kernel<LOG2N, Tin, MODE>, BP::NT, BP::SMEM, BP::FPC, a, stream,
                               dynamic_units);
@@ -41,36 +46,42 @@ struct CudaLauncher {
     bool dynamic_units = true;       // all FFT kernel families: atomic work counter instead of static round-robin (large launches)
     template <typename Tin, int S, int MODE>
     int duo256(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_duo256_kernel (frame duo, 8 lanes)", a);
         using DP = Duo256Plan;
         return b2s_launch_any((const void*)stft_psd_duo256_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream,
                               dynamic_units);
     }
     template <int LOG2N, typename Tin, int S, int MODE>
     int duo4(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_duo4_kernel (four-step frame duo)", a);
         using DP = Duo4Plan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_duo4_kernel<LOG2N, Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
                               stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int duo_cta(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_duo_cta_kernel (frame duo per CTA group)", a);
         using DP = DuoCtaPlan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_duo_cta_kernel<LOG2N, Tin, MODE>, DP::NT, DP::SMEM, DP::FPC, a,
                               stream, dynamic_units);
     }
     template <typename Tin, int S, int MODE>
     int duo(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_duo_kernel (frame duo, 16 lanes)", a);
         using DP = DuoPlan;
         return b2s_launch_any((const void*)stft_psd_duo_kernel<Tin, S, MODE>, DP::NT, DP::SMEM, DP::FPC, a, stream,
                               dynamic_units);
     }
     template <int LOG2N, typename Tin, int SHIFT, int MODE>
     int warp(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_warp_kernel (one frame per lane group)", a);
         using WP = WarpPlan<LOG2N>;
         return b2s_launch_any((const void*)stft_psd_warp_kernel<LOG2N, Tin, SHIFT, MODE>, WP::NT, WP::SMEM,
                               WP::FPC, a, stream, dynamic_units);
     }
     template <int LOG2N, typename Tin, int MODE>
     int cta(const StftArgs& a) {
+        b2s_note_kernel("stft_psd_kernel (one frame per thread group)", a);
         using PL = Plan<LOG2N>;
         constexpr int MINB = (PL::NT <= 256) ? 2 : 1;
         return b2s_launch_any((const void*)stft_psd_kernel<LOG2N, Tin, MINB, MODE>, PL::NT, PL::SMEM, PL::FPC,

@@ -87,7 +87,7 @@ def mean_spectrogram_sharded(x_local, total_sweeps: int, fs=1.0, window=("tukey"
                                    sum_out=reducer.partial() if use_peer else None)
         if use_peer:
             mean = reducer.reduce(1.0 / float(total_sweeps)).view(S.shape[1:])
-            reducer.wait()                       # overlap mode: the result is used on this stream right away
+            reducer.check()                      # joins the side stream; raises if a rank missed the time-out
         else:
             if ws > 1:
                 dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
@@ -253,3 +253,13 @@ class PeerMeanReducer:
         """Overlap mode: make the current stream wait for every reduce issued so far."""
         if self.overlap:
             torch.cuda.current_stream(self.device).wait_stream(self.side)
+
+    def check(self):
+        """Synchronise and raise ``TimeoutError`` if a reduce gave up waiting for a late rank
+        (``B2S_PEER_TIMEOUT_MS``, default two minutes of wall-clock time; its output was not
+        written).  Every rank must enqueue ``reduce`` within that window of its peers."""
+        from . import _lib
+        self.wait()
+        with torch.cuda.device(self.device):
+            rc = self._lib.b2s_peer_allreduce_status(torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_peer_allreduce_status")

@@ -123,27 +123,48 @@ def triage(n, fs, window, nperseg, noverlap, nfft, detrend, return_onesided, sca
 # device engine
 # --------------------------------------------------------------------------
 
+def _dev_index(device) -> int:
+    """Explicit CUDA device index (``torch.device('cuda')`` has index None: the current device)."""
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else int(device.index)
+
+
 class Engine:
     """Per-process state: the loaded library and per-device window tables."""
 
+    _MAX_WINDOWS = 64
+
     def __init__(self):
         self._lock = threading.Lock()
-        self._windows = {}
+        self._windows = {}            # insertion-ordered: least recently used first
 
     @staticmethod
     def require_cuda():
         if not torch.cuda.is_available():
             raise _lib.B2SError("no CUDA device: the spectrogram engine has no CPU fallback")
 
+    # The kernels fold sqrt(scale/2) into the window taps (|2 X|^2 is then the PSD of an interior bin).
+    # Done on the device that would round every fp32 tap a second time, and at the error level of this
+    # path (rms 2e-6 of a bin 60 dB under a tone) a per-sample relative error of 2^-25 is measurable.
+    # So the fold happens HERE, in float64, with ONE rounding to fp32, and the library is called with
+    # scale = KERNEL_SCALE = 2: its sqrt(scale/2) is then exactly 1.
+    KERNEL_SCALE = 2.0
+
     def window_table(self, plan: Plan, device: torch.device) -> torch.Tensor:
-        key = (plan.window_key, device.index)
+        """fp32 taps ``w * sqrt(scale/2)`` (folded in float64, rounded once) on ``device``; pass
+        ``KERNEL_SCALE`` as the scale of every library call that uses them."""
+        idx = _dev_index(device)
+        key = (plan.window_key, float(plan.scale), idx)
         with self._lock:
-            t = self._windows.get(key)
+            t = self._windows.pop(key, None)
             if t is None:
-                if len(self._windows) > 64:
-                    self._windows.clear()
-                t = torch.from_numpy(plan.win64.astype(np.float32)).to(device)
-                self._windows[key] = t
+                # evict the least recently used table; kernels still reading it keep it alive through
+                # the caching allocator's stream ordering (it was created and is used on this device's streams)
+                while len(self._windows) >= self._MAX_WINDOWS:
+                    self._windows.pop(next(iter(self._windows)))
+                taps = (plan.win64 * np.sqrt(0.5 * plan.scale)).astype(np.float32)
+                t = torch.from_numpy(taps).to(torch.device("cuda", idx))
+            self._windows[key] = t                      # (re)insert as most recently used
             return t
 
     def stft_psd(self, x: torch.Tensor, plan: Plan, *, out=None, out_mode=0, db_floor=0.0,
@@ -178,7 +199,7 @@ class Engine:
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop,
-                    win.data_ptr(), plan.detrend, plan.scale, int(out_mode), float(db_floor),
+                    win.data_ptr(), plan.detrend, self.KERNEL_SCALE, int(out_mode), float(db_floor),
                     int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
                     nframes * kout, stream)
         _lib.check(rc, "b2s_stft_psd")
@@ -219,7 +240,7 @@ class Engine:
         fn = lib.b2s_stft_psd_sum_f32 if x.dtype == torch.float32 else lib.b2s_stft_psd_sum_f64
         with torch.cuda.device(x.device):
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
-                    plan.detrend, plan.scale, 0, F, out.data_ptr(), F * K, sum_out.data_ptr(), float(post_scale),
+                    plan.detrend, self.KERNEL_SCALE, 0, F, out.data_ptr(), F * K, sum_out.data_ptr(), float(post_scale),
                     scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b2s_stft_psd_sum")
         return out, sum_out
@@ -227,12 +248,14 @@ class Engine:
     def _sum_scratch(self, elems: int, device) -> torch.Tensor:
         """Partial-sum scratch of the sum-fused path, kept per device (stream-ordered reuse: the
         kernels that touch it are enqueued on the caller's current stream)."""
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        key = (_dev_index(device), torch.cuda.current_stream(device).cuda_stream)
         cache = self.__dict__.setdefault("_scratch", {})
-        t = cache.get(key)
+        t = cache.pop(key, None)
         if t is None or t.numel() < elems:
             t = torch.empty(max(int(elems), 1), dtype=torch.float32, device=device)
-            cache[key] = t
+        while len(cache) >= 16:                         # streams come and go: keep the most recent few
+            cache.pop(next(iter(cache)))
+        cache[key] = t
         return t
 
     def band_power(self, x: torch.Tensor, plan: Plan, kmin: int, kmax: int, *, frame0=0, nframes=None) -> torch.Tensor:
@@ -256,7 +279,7 @@ class Engine:
         fn = lib.b2s_stft_band_power_f32 if x.dtype == torch.float32 else lib.b2s_stft_band_power_f64
         with torch.cuda.device(x.device):
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
-                    plan.detrend, plan.scale, int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
+                    plan.detrend, self.KERNEL_SCALE, int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
                     nframes, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b2s_stft_band_power")
         return out
@@ -370,16 +393,17 @@ class _Streams:
 
     @classmethod
     def get(cls, dev: torch.device):
-        s = cls._by_dev.get(dev.index)
+        idx = _dev_index(dev)
+        s = cls._by_dev.get(idx)
         if s is None:
-            with torch.cuda.device(dev):
+            with torch.cuda.device(idx):
                 s = (torch.cuda.Stream(), torch.cuda.Stream())
-            cls._by_dev[dev.index] = s
+            cls._by_dev[idx] = s
         return s
 
 
 def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=True, want_sum=False,
-                   sum_scale=1.0, kmin=0, kmax=None, out_mode=0, db_floor=0.0):
+                   sum_scale=1.0, kmin=0, kmax=None, out_mode=0, db_floor=0.0, host_out=None):
     """Host arrays in, host arrays out: H2D copy, kernels and D2H copy of successive
     chunks overlap on three streams (PCIe is full duplex), so the end-to-end time tends
     to max(H2D, D2H) instead of their sum.  Chunks are runs of sweeps for batches and
@@ -403,7 +427,15 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
         # for 1000 x 40001 samples)
         x_d = torch.empty((B, n + (n & 1)), dtype=h_in.dtype, device=dev)[:, :n]
         S_d = torch.empty((B, F, kout), dtype=torch.float32, device=dev)
-        h_out = torch.empty((B, F, kout), dtype=torch.float32, pin_memory=True) if per_sweep else None
+        h_out = None
+        if per_sweep:
+            if host_out is not None:
+                # caller-owned result buffer (ideally page-locked, see pinned_empty): reused across calls
+                if host_out.shape != (B, F, kout) or host_out.dtype != np.float32 or not host_out.flags.c_contiguous:
+                    raise ValueError(f"out must be a C-contiguous float32 array of shape {(B, F, kout)}")
+                h_out = torch.from_numpy(host_out)
+            else:
+                h_out = torch.empty((B, F, kout), dtype=torch.float32, pin_memory=True)
         row_bytes = F * kout * 4
         # work items: (b0, b1, f0, f1)
         items = []
@@ -527,11 +559,17 @@ def spectrogram_batch(x, fs=1.0, **kw):
 
 def mean_spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=None, nfft=None,
                      detrend="constant", return_onesided=True, scaling="density", mode="psd",
-                     *, return_per_sweep=False, device=None):
+                     *, return_per_sweep=False, device=None, out=None, group=None, total_sweeps=None):
     """Cross-sweep mean spectrogram of ``x[B, N]``: ``mean_b Sxx_b`` (BASELINE
     config 2; the reference has no code for it -- SURVEY.md 8 a-15).  The sum
     over sweeps runs on the device in a fixed order.  Returns ``(f, t, Smean[K, F])``
-    or, with ``return_per_sweep``, ``(f, t, Smean, Sxx[B, K, F])``."""
+    or, with ``return_per_sweep``, ``(f, t, Smean, Sxx[B, K, F])``.
+
+    ``out``: a caller-owned float32 ``[B, F, K]`` result buffer for the per-sweep spectrograms (page-locked
+    memory from :func:`pinned_empty` makes the copy back asynchronous); reuse it across calls instead
+    of paying for a fresh 318 MB pinned allocation every time.  ``group`` / ``total_sweeps``: ``x`` holds
+    this rank's sweeps of a batch sharded over the ranks of a ``torch.distributed`` group; the partial
+    sums are all-reduced before the division, every rank returns the global mean."""
     x, out_dtype, is_complex = _prepare_input(x, -1)
     if x.ndim != 2:
         raise ValueError("mean_spectrogram expects x of shape [B, N]")
@@ -544,9 +582,14 @@ def mean_spectrogram(x, fs=1.0, window=("tukey", .25), nperseg=None, noverlap=No
     eng = engine()
     eng.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    import torch.distributed as dist
+    sharded = group is not None or (total_sweeps is not None and dist.is_available() and dist.is_initialized())
+    n_total = int(total_sweeps) if total_sweeps is not None else x.shape[0]
     S, total = _host_pipeline(x, plan, dev, out_dtype, per_sweep=return_per_sweep, want_sum=True,
-                              sum_scale=1.0 / x.shape[0])
+                              sum_scale=1.0 / n_total, host_out=out)
     with torch.cuda.device(dev):
+        if sharded and dist.get_world_size(group) > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)      # sum of partial means
         mean = np.moveaxis(_to_host(total, out_dtype), -1, -2)
     if return_per_sweep:
         return f, t, mean, np.moveaxis(S, -1, -2)

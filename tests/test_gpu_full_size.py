@@ -1,0 +1,115 @@
+"""BASELINE.json's configs at their FULL sizes, every row / channel / frame against the float64
+oracle (scipy.signal.spectrogram as the reference calls it, in chunks), with SciPy's own float32
+pipeline -- what the reference runs when it is fed float32 samples -- measured beside it on the
+same data.  The bar (util.assert_parity_full):
+
+  * |dS| <= 1e-6 * max(S) everywhere, time / frequency axes bit-exact;
+  * at most 1e-5 of the bins above the floor (S >= 1e-6 max) may miss rel 1e-4 at all, and
+  * no bin may miss it by more than 1.25 x the worst bin of SciPy-float32 on the same data
+    (or 1.25e-4 where SciPy-float32 itself stays under 1e-4);
+  * the error distribution (RMS, 99.99th percentile) is no wider than 1.15 x / 1.25 x SciPy-float32's.
+"""
+import numpy as np
+import pytest
+import scipy.signal
+import torch
+
+import spectrogram_generator_b200 as sg
+from spectrogram_generator_b200 import synth
+from util import FullSizeStats
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_all_1000_sweeps_and_the_mean():
+    x, kw = synth.config2(batch=1000)
+    fs = kw.pop("fs")
+    f, t, m, S = sg.mean_spectrogram(x, fs=fs, return_per_sweep=True, **kw)
+    assert S.shape == (1000, 257, 309)
+    st = FullSizeStats("C2 1000 x 40000 @ 512/128")
+    mean64 = np.zeros((257, 309))
+    for lo in range(0, 1000, 100):
+        fo, to, So = scipy.signal.spectrogram(x[lo:lo + 100].astype(np.float64), fs=fs, **kw)
+        S32 = scipy.signal.spectrogram(x[lo:lo + 100], fs=fs, **kw)[2]
+        assert np.array_equal(f, fo) and np.array_equal(t, to)
+        st.add(S[lo:lo + 100], So, S32)
+        mean64 += So.sum(axis=0)
+    st.check()
+    mean64 /= 1000
+    assert np.max(np.abs(m - mean64)) <= 1e-6 * mean64.max()
+    big = mean64 >= 1e-6 * mean64.max()
+    assert np.max(np.abs(m[big] - mean64[big]) / mean64[big]) <= 1e-5       # averaging 1000 sweeps: far inside the bar
+
+
+def test_config4_sixteen_channels_sixty_seconds():
+    x, kw = synth.config4(seconds=60.0)
+    fs = kw.pop("fs")
+    f, t, S = sg.spectrogram(x, fs=fs, **kw)
+    assert S.shape == (16, 2049, 5622)
+    st = FullSizeStats("C4 16 x 5.76 M @ 4096/1024")
+    for c in range(16):
+        fo, to, So = scipy.signal.spectrogram(x[c].astype(np.float64), fs=fs, **kw)
+        S32 = scipy.signal.spectrogram(x[c], fs=fs, **kw)[2]
+        assert np.array_equal(f, fo) and np.array_equal(t, to)
+        st.add(S[c], So, S32)
+        assert abs(f[np.argmax(S[c].mean(axis=1))] - 1000.0 * (c + 1)) <= fs / 4096
+    st.check()
+
+
+def test_config3_the_whole_hour():
+    x, kw = synth.config3()                      # 172.8 M samples
+    fs = kw.pop("fs")
+    plan = sg.triage(x.shape[0], fs, kw["window"], kw["nperseg"], kw["noverlap"], None, "constant", True,
+                     "density", "psd")
+    assert plan.nframes == 337497
+    eng = sg.engine()
+    S = eng.stft_psd(torch.from_numpy(x).cuda().view(1, -1), plan)[0]         # [F, K] on the device
+    t = sg.windows.time_axis(plan.n, plan.nperseg, plan.noverlap, fs)
+    st = FullSizeStats("C3 172.8 M @ 2048/512")
+    for f0, c in sg.split_frames(plan.nframes, 24):
+        lo, hi = f0 * plan.hop, (f0 + c - 1) * plan.hop + plan.nperseg
+        fo, to, So = scipy.signal.spectrogram(x[lo:hi].astype(np.float64), fs=fs, **kw)
+        S32 = scipy.signal.spectrogram(x[lo:hi], fs=fs, **kw)[2]
+        # the chunk's own time axis starts at nperseg/2; the global one is cut from the global recipe
+        assert np.allclose(t[f0:f0 + c] - t[f0], to - to[0], rtol=0, atol=1e-9)
+        st.add(S[f0:f0 + c].T.cpu().numpy(), So, S32)
+    st.check()
+    # the frame ranges 8 ranks would own: identical bits
+    for f0, c in sg.split_frames(plan.nframes, 8)[::3]:
+        lo, hi = f0 * plan.hop, (f0 + c - 1) * plan.hop + plan.nperseg
+        sub = sg.Plan(**{**plan.__dict__, "n": hi - lo, "nframes": c})
+        assert torch.equal(eng.stft_psd(torch.from_numpy(x[lo:hi]).cuda().view(1, -1), sub)[0], S[f0:f0 + c])
+
+
+def test_config1_fused_db_epilogue_on_the_device():
+    """C1 through Engine.stft_psd(out_mode=1): 10 log10(max(S, floor)) inside the kernel's store."""
+    x, kw = synth.config1()
+    fs = kw.pop("fs")
+    plan = sg.triage(x.shape[0], fs, kw["window"], kw["nperseg"], kw["noverlap"], None, "constant", True,
+                     "density", "psd")
+    fo, to, So = scipy.signal.spectrogram(x.astype(np.float64), fs=fs, **kw)
+    floor = float(1e-6 * So.max())
+    db = sg.engine().stft_psd(torch.from_numpy(x).cuda().view(1, -1), plan, out_mode=1, db_floor=floor)[0]
+    assert db.shape == (1719, 513)
+    ref = 10.0 * np.log10(np.maximum(So, floor))
+    got = db.T.cpu().numpy().astype(np.float64)
+    big = So >= floor
+    assert np.max(np.abs(got[big] - ref[big])) <= 1e-3
+    assert np.max(np.abs(got[~big] - ref[~big])) <= 1e-3          # below the floor both sit on 10 log10(floor)
+    S32 = scipy.signal.spectrogram(x, fs=fs, **kw)[2]
+    st = FullSizeStats("C1 441000 @ 1024/256")
+    st.add(sg.spectrogram(x, fs=fs, **kw)[2], So, S32)
+    st.check()
+
+
+@pytest.mark.parametrize("nperseg", [256, 1024, 4096, 16384])
+def test_config5_points_at_batch_64(nperseg):
+    x, kw = synth.config5(nperseg, 0.75, batch=64)
+    fs = kw.pop("fs")
+    f, t, S = sg.spectrogram(x, fs=fs, **kw)
+    fo, to, So = scipy.signal.spectrogram(x.astype(np.float64), fs=fs, **kw)
+    S32 = scipy.signal.spectrogram(x, fs=fs, **kw)[2]
+    assert np.array_equal(f, fo) and np.array_equal(t, to)
+    st = FullSizeStats(f"C5 64 x 100000 @ {nperseg}/75 %")
+    st.add(S, So, S32)
+    st.check()

@@ -54,6 +54,74 @@ def assert_parity(S, So, rel=REL_TOL, floor=FLOOR, abs_tol=ABS_TOL, db=DB_TOL, w
     return r
 
 
+class _Stream:
+    """Streaming max / rms / quantile (log-spaced histogram, 0.25 % resolution) of relative errors."""
+    EDGES = np.logspace(-10, -1, 3601)
+
+    def __init__(self):
+        self.n, self.sumsq, self.max, self.hist = 0, 0.0, 0.0, np.zeros(3602, dtype=np.int64)
+
+    def add(self, r, rel):
+        r = np.asarray(r, dtype=np.float64).ravel()
+        self.n += r.size
+        self.sumsq += float(np.dot(r, r))
+        if r.size:
+            self.max = max(self.max, float(r.max()))
+        self.hist += np.bincount(np.searchsorted(self.EDGES, r), minlength=3602)
+        self.over = getattr(self, "over", 0) + int(np.count_nonzero(r > rel))
+
+    def quantile(self, q):
+        c = np.cumsum(self.hist)
+        i = int(np.searchsorted(c, q * self.n))
+        return float(self.EDGES[min(i, 3600)])                   # upper edge of the bin
+
+    def summary(self):
+        return dict(max=self.max, rms=float(np.sqrt(self.sumsq / max(self.n, 1))), p9999=self.quantile(0.9999),
+                    frac_over=self.over / max(self.n, 1))
+
+
+class FullSizeStats:
+    """Error statistics of the engine and of SciPy's own float32 pipeline against the float64 oracle,
+    accumulated over chunks of a full-size configuration (tests/test_gpu_full_size.py)."""
+
+    def __init__(self, what, rel=REL_TOL):
+        self.what, self.rel = what, rel
+        self.ours, self.theirs = _Stream(), _Stream()
+        self.abs_ours = 0.0
+        self.n_bins = 0
+
+    def add(self, S, So, S32, floor=FLOOR):
+        So = np.asarray(So, dtype=np.float64)
+        assert S.shape == So.shape == S32.shape, (S.shape, So.shape, S32.shape)
+        if So.ndim > 2:                           # a batch: every sweep / channel has its own floor
+            for i in range(So.shape[0]):
+                self.add(S[i], So[i], S32[i], floor)
+            return
+        S, S32 = np.asarray(S, dtype=np.float64), np.asarray(S32, dtype=np.float64)
+        assert np.isfinite(S).all()
+        peak = So.max()
+        big = (So >= floor * peak) & (So > 0)
+        d = np.abs(S - So)
+        self.ours.add(d[big] / So[big], self.rel)
+        self.theirs.add(np.abs(S32 - So)[big] / So[big], self.rel)
+        self.abs_ours = max(self.abs_ours, float(d.max() / peak))
+        self.n_bins += So.size
+
+    def check(self, abs_tol=ABS_TOL, tail=1e-5):
+        rel = self.rel
+        rep = dict(what=self.what, bins=self.n_bins, above_floor=self.ours.n, ours=self.ours.summary(),
+                   scipy_f32=self.theirs.summary())
+        print("\nFULLSIZE", {k: ({kk: float(f"{vv:.4g}") for kk, vv in v.items()} if isinstance(v, dict) else v)
+                             for k, v in rep.items()})
+        assert self.abs_ours <= abs_tol, f"{self.what}: abs err {self.abs_ours:.3e} * max"
+        assert rep["ours"]["frac_over"] <= tail, f"{self.what}: {rep['ours']['frac_over']:.2e} of the bins miss rel {rel}"
+        bar = 1.25 * max(rel, rep["scipy_f32"]["max"])
+        assert rep["ours"]["max"] <= bar, f"{self.what}: worst bin {rep['ours']['max']:.3e} > {bar:.3e}"
+        assert rep["ours"]["rms"] <= 1.15 * rep["scipy_f32"]["rms"], f"{self.what}: rms {rep}"
+        assert rep["ours"]["p9999"] <= 1.25 * rep["scipy_f32"]["p9999"], f"{self.what}: p99.99 {rep}"
+        return rep
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     d = {k: z[k] for k in z.files}
@@ -83,18 +151,27 @@ class Emulator:
         self.lib.emu_batch_sum.argtypes = [c.c_void_p, c.c_longlong, c.c_int, c.c_int, c.c_longlong,
                                            c.c_void_p, c.c_float]
 
+    @staticmethod
+    def taps(plan, prescale):
+        """(fp32 window table, scale) as the host layer passes them (Engine.window_table: sqrt(scale/2)
+        folded in float64, scale = 2), or -- prescale=False -- raw taps and the true scale, the other
+        form the C ABI accepts."""
+        if prescale:
+            return (plan.win64 * np.sqrt(0.5 * plan.scale)).astype(np.float32), 2.0
+        return plan.win64.astype(np.float32), plan.scale
+
     def stft_psd(self, x2d, plan, out_mode=0, db_floor=0.0, kmin=0, kmax=None, frame0=0, nframes=None,
-                 grid=2, chunk=0):
+                 grid=2, chunk=0, prescale=True):
         x2d = np.ascontiguousarray(x2d)
         assert x2d.dtype in (np.float32, np.float64) and x2d.ndim == 2
         B, n = x2d.shape
         kmax = plan.nbins - 1 if kmax is None else kmax
         nframes = plan.nframes - frame0 if nframes is None else nframes
         kout = kmax - kmin + 1
-        w = plan.win64.astype(np.float32)
+        w, scale = self.taps(plan, prescale)
         out = np.full((B, nframes, kout), np.nan, np.float32)
         rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
-                                   plan.hop, w.ctypes.data, plan.detrend, plan.scale, out_mode, db_floor,
+                                   plan.hop, w.ctypes.data, plan.detrend, scale, out_mode, db_floor,
                                    kmin, kmax, frame0, nframes, out.ctypes.data, nframes * kout, grid, chunk, 0)
         assert rc == 0, rc
         return out
@@ -103,10 +180,10 @@ class Emulator:
         x2d = np.ascontiguousarray(x2d)
         B, n = x2d.shape
         nframes = plan.nframes - frame0 if nframes is None else nframes
-        w = plan.win64.astype(np.float32)
+        w, scale = self.taps(plan, True)
         out = np.full((B, nframes), np.nan, np.float32)
         rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
-                                   plan.hop, w.ctypes.data, plan.detrend, plan.scale, 0, 0.0,
+                                   plan.hop, w.ctypes.data, plan.detrend, scale, 0, 0.0,
                                    kmin, kmax, frame0, nframes, out.ctypes.data, nframes, grid, chunk, 1)
         assert rc == 0, rc
         return out
@@ -123,7 +200,7 @@ class Emulator:
         x2d = np.ascontiguousarray(x2d)
         B, n = x2d.shape
         F, K = plan.nframes, plan.nbins
-        w = plan.win64.astype(np.float32)
+        w, scale = self.taps(plan, True)
         out = np.full((B, F, K), np.nan, np.float32)
         tot = np.full((F, K), np.nan, np.float32)
         c = ctypes
@@ -133,7 +210,7 @@ class Emulator:
                        c.c_int, c.c_double, c.c_longlong, c.c_longlong, c.c_void_p, c.c_longlong, c.c_void_p,
                        c.c_float, c.c_int, c.c_int]
         rc = fn(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg, plan.hop, w.ctypes.data,
-                plan.detrend, plan.scale, 0, F, out.ctypes.data, F * K, tot.ctypes.data, post_scale, grid, max_blocks)
+                plan.detrend, scale, 0, F, out.ctypes.data, F * K, tot.ctypes.data, post_scale, grid, max_blocks)
         assert rc > 0, rc
         return out, tot, rc
 
