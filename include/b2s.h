@@ -196,6 +196,18 @@ int b2s_stft_psd_sum_f64(const double* x, long long batch, long long n, long lon
 int b2s_display_scale_f32(const float* s, long long elems, int log_scale, float global_max, float* out,
                           unsigned int* scratch, void* stream);
 
+/* Power summaries of the spectrogram the path left on the device -- the reductions of
+ * PlotEngine.calculate_absolute_power (PlotEngine.py:686-690: sum(last_Sxx)) and
+ * PlotEngine.calculate_band_powers (PlotEngine.py:692-719: sum over the rows of last_f in
+ * [low, high) of max(0, last_Sxx), divided by the total on the host).  s: device [frames][bins]
+ * (the cropped result of b2s_stft_psd_*); k0/k1: HOST arrays of nb <= 16 half-open bin ranges
+ * [k0, k1) (empty ranges allowed); out: device, nb + 1 doubles -- the band sums, then the total
+ * over all bins; scratch: device, b2s_band_sums_scratch_elems() doubles.  Fixed summation order,
+ * double accumulators; negative values are clamped to 0 like the reference's np.maximum. */
+long long b2s_band_sums_scratch_elems(void);
+int b2s_band_sums_f32(const float* s, long long frames, int bins, const int* k0, const int* k1, int nb, double* out,
+                      double* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,7 +11,7 @@ in ``include/b2s.h``); importing the package does not need a GPU, calling it doe
 from .spectrogram import (Engine, Plan, engine, mean_spectrogram, pinned_empty, spectrogram,
                           spectrogram_batch, spectrogram_chunked, split_frames, triage)
 from .plot_engine import SpectrogramPath
-from . import distributed, synth, windows
+from . import distributed, plot_engine, synth, windows
 
 __all__ = ["spectrogram", "spectrogram_batch", "mean_spectrogram", "spectrogram_chunked",
            "split_frames", "pinned_empty", "engine", "Engine", "Plan", "triage",

@@ -109,6 +109,8 @@ SIGNATURES = {
     "b2s_batch_sum_scratch_elems": (c_longlong, [c_longlong, c_longlong]),
     "b2s_batch_sum_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p,
                                   c_float, c_void_p]),
+    "b2s_band_sums_scratch_elems": (c_longlong, []),
+    "b2s_band_sums_f32": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "b2s_display_scale_f32": (c_int, [c_void_p, c_longlong, c_int, c_float, c_void_p, c_void_p, c_void_p]),
 }
 

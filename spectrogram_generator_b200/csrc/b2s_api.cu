@@ -229,25 +229,31 @@ struct PairState {
 };
 std::map<std::pair<const void*, long long>, PairState> g_pair;     // (kernel, device << 32 | smem) -> residency
 
-int launch_pair_impl(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
-                     bool dynamic) {
+int launch_pair_impl(const void* kern, const void* kern_mid, const void* kern_wide, int esz, const b2s::StftArgs& a,
+                     cudaStream_t stream, bool dynamic) {
     using PP = b2s::PairPlan<10>;
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-    // CTA shape: 128 threads (several CTAs per SM, 168 registers) or one wide CTA per SM (136 registers,
-    // as many warps as its shared memory allows); B2S_PAIR_NT / b2s_set_option("pair_nt") overrides
-    // Measured on B200 (tools/microbench.py --set n1024x, profiles/r2_pair_cta_width.md): one wide CTA per SM
-    // (the constant tables once per SM, up to 15 warps at 128 registers) wins from hop 512 down and with
-    // little overlap, where three 128-thread CTAs no longer fit their rings (hop 1024: 0.70 -> 0.81 of the HBM peak).
-    int nt = (a.hop > 768) ? 384 : 480;
-    if (a.batch * a.nframes < 64 * di.sm_count) nt = PP::NT;      // small launches: more, smaller CTAs
+    // CTA shape (B2S_PAIR_NT / b2s_set_option("pair_nt") overrides).  Nothing in the main loop is CTA-wide, so
+    // the shape only decides how many warps share an SM and how many registers each gets.  Measured on B200
+    // (tools/microbench.py --set n1024x, profiles/r2_pair_cta_width.md):
+    //   128 x 3 CTAs (164 registers)  the default;
+    //   192 x 2 CTAs (168 registers)  hop > 768: three 128-thread CTAs no longer fit their rings there;
+    //   one CTA of 480 (128 registers) hop <= 128 and 257..768: 15 warps per SM buy up to 10 %.
+    int nt = PP::NT;
+    const bool big_launch = a.batch * a.nframes >= 64LL * di.sm_count;
+    if (big_launch) {
+        if (a.hop > 768) nt = PP::NT_MID;
+        else if (a.hop <= 128 || a.hop > 256) nt = 480;
+    }
     if (env().pair_nt > 0) nt = env().pair_nt / 32 * 32;
     if (nt < 32) nt = 32;
     if (nt > PP::NT_WIDE) nt = PP::NT_WIDE;
-    while (nt > PP::NT && (int)PP::smem_bytes(a.hop, esz, nt) > di.smem_optin) nt -= 32;
-    if (nt > PP::NT) kern = kern_wide;
+    while (nt > PP::NT_MID && (int)PP::smem_bytes(a.hop, esz, nt) > di.smem_optin) nt -= 32;
+    if (nt > PP::NT_MID) kern = kern_wide;
+    else if (nt > PP::NT) kern = kern_mid;
     const size_t smem = PP::smem_bytes(a.hop, esz, nt);
     if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this hop");
     int occ = 0;
@@ -457,9 +463,9 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
     return launch_any_impl(kern, nt, smem, fpc, a, stream, false, dynamic);
 }
 
-int b2s_launch_pair(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
-                    bool dynamic) {
-    return launch_pair_impl(kern, kern_wide, esz, a, stream, dynamic);
+int b2s_launch_pair(const void* kern, const void* kern_mid, const void* kern_wide, int esz, const b2s::StftArgs& a,
+                    cudaStream_t stream, bool dynamic) {
+    return launch_pair_impl(kern, kern_mid, kern_wide, esz, a, stream, dynamic);
 }
 
 extern "C" {
@@ -622,6 +628,30 @@ int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned l
                                                                          vec_ok, timeout_ns, err_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce_kernel launch");
+    return B2S_OK;
+}
+
+long long b2s_band_sums_scratch_elems(void) { return 256LL * (b2s::kMaxBands + 1); }
+
+int b2s_band_sums_f32(const float* s, long long frames, int bins, const int* k0, const int* k1, int nb, double* out,
+                      double* scratch, void* stream) {
+    if (!s || !out || !scratch || frames < 1 || bins < 1 || nb < 0 || nb > b2s::kMaxBands || (nb > 0 && (!k0 || !k1)))
+        return fail(B2S_ERR_BAD_ARG, "b2s_band_sums_f32: bad argument");
+    b2s::BandRanges br{};
+    for (int b = 0; b < nb; ++b) {
+        if (k0[b] < 0 || k1[b] > bins || k0[b] > k1[b])
+            return fail(B2S_ERR_BAD_ARG, "b2s_band_sums_f32: band outside [0, bins]");
+        br.k0[b] = k0[b];
+        br.k1[b] = k1[b];
+    }
+    br.k0[nb] = 0;
+    br.k1[nb] = bins;
+    const int blocks = (int)(frames < 256 ? frames : 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    b2s::band_sums_kernel<<<blocks, 256, 0, st>>>(s, frames, bins, br, nb, scratch);
+    b2s::band_sums_fold_kernel<<<1, 32, 0, st>>>(scratch, blocks, nb, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "band_sums kernels");
     return B2S_OK;
 }
 

@@ -171,4 +171,43 @@ B2S_GLOBAL void display_scale_kernel(const float* __restrict__ s, long long elem
     }
 }
 
+
+// ---- power summaries (PlotEngine.calculate_absolute_power / calculate_band_powers, PlotEngine.py:686-719) ----
+// s is the [frames][bins] spectrogram the path left on the device (already cropped to the displayed
+// band); band b is the bin range [k0[b], k1[b]) (may be empty), band nb the whole row (the total).
+// Negative values are clamped to 0 as the reference does (np.maximum(0, Sxx)).  Two launches, fixed
+// summation order, double accumulators: block x sums the frames x, x + gridDim.x, ... (one warp per
+// band, lanes stride the bins, xor-butterfly), then one block folds the per-block partials.
+constexpr int kMaxBands = 16;
+struct BandRanges {
+    int k0[kMaxBands + 1];
+    int k1[kMaxBands + 1];
+};
+
+B2S_GLOBAL void band_sums_kernel(const float* __restrict__ s, long long frames, int bins, const BandRanges br,
+                                 int nb, double* __restrict__ partial) {
+    const int warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+    const int nwarps = (int)blockDim.x >> 5;
+    for (int b = warp; b <= nb; b += nwarps) {
+        double acc = 0.0;
+        for (long long f = blockIdx.x; f < frames; f += gridDim.x) {
+            const float* row = s + f * bins;
+            double a = 0.0;
+            for (int k = br.k0[b] + lane; k < br.k1[b]; k += 32) a += (double)fmaxf(row[k], 0.f);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            acc += a;
+        }
+        if (lane == 0) partial[(long long)blockIdx.x * (kMaxBands + 1) + b] = acc;
+    }
+}
+
+B2S_GLOBAL void band_sums_fold_kernel(const double* __restrict__ partial, int nblocks, int nb, double* __restrict__ out) {
+    const int b = (int)threadIdx.x;
+    if (b > nb) return;
+    double acc = 0.0;
+    for (int i = 0; i < nblocks; ++i) acc += partial[(long long)i * (kMaxBands + 1) + b];
+    out[b] = acc;
+}
+
 }  // namespace b2s

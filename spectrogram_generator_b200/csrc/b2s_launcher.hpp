@@ -14,8 +14,8 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
                    bool dynamic = false);
 
 // One launch of the staged-sample pair kernel (b2s_pair_kernel.cuh).  Defined in b2s_api.cu.
-int b2s_launch_pair(const void* kern, const void* kern_wide, int esz, const b2s::StftArgs& a, cudaStream_t stream,
-                    bool dynamic);
+int b2s_launch_pair(const void* kern, const void* kern_mid, const void* kern_wide, int esz, const b2s::StftArgs& a,
+                    cudaStream_t stream, bool dynamic);
 
 // Records which kernel the calling thread launched last (b2s_last_kernel() in include/b2s.h).
 void b2s_note_kernel(const char* family, const b2s::StftArgs& a);
@@ -33,6 +33,7 @@ struct CudaLauncher {
     int pair(const StftArgs& a) {
         b2s_note_kernel("stft_psd_pair_kernel (staged samples: TMA ring, sub-sequence pairs in fp32x2)", a);
         return b2s_launch_pair((const void*)stft_psd_pair_kernel<LOG2N, Tin, MODE>,
+                               (const void*)stft_psd_pair_mid_kernel<LOG2N, Tin, MODE>,
                                (const void*)stft_psd_pair_wide_kernel<LOG2N, Tin, MODE>,
                                (int)sizeof(Tin), a, stream, dynamic_units);
     }

@@ -49,6 +49,7 @@ struct PairPlan {
     // (<= 136 registers): nothing in the main loop is CTA-wide, so the CTA is only the unit that shares
     // the constant tables.  `nt` below is the launch's block size.
     static constexpr int NT = 128;
+    static constexpr int NT_MID = 192;
     static constexpr int NT_WIDE = 512;
     static constexpr int ROW = 17, BUF = 16 * ROW;       // transpose buffer of one frame, float4 units
     // shared memory, float4 units
@@ -177,6 +178,12 @@ template <int LOG2N, typename Tin, int MODE>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(512, 1) stft_psd_pair_wide_kernel(const StftParams p) {
     stft_psd_pair_body<LOG2N, Tin, MODE, 1>(p);
 }
+// 192 threads x 2 CTAs per SM (168 registers): twelve warps where three 128-thread CTAs no longer fit
+// their rings (hop > 768)
+template <int LOG2N, typename Tin, int MODE>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(192, 2) stft_psd_pair_mid_kernel(const StftParams p) {
+    stft_psd_pair_body<LOG2N, Tin, MODE, 2>(p);
+}
 
 template <int LOG2N, typename Tin, int MODE, int MINB>
 B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
@@ -200,9 +207,6 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
 
     // ---- constant tables, once per CTA; the PSD scale goes into the window ----
     {
-        // (the host layer passes taps that already carry sqrt(scale/2), folded in double and rounded once,
-        //  with scale = 2: csc is then exactly 1 -- a second rounding of every tap is measurable in the bins
-        //  60 dB under a tone)
         const float csc = sqrtf(0.5f * p.scale);
         const float4* w4 = reinterpret_cast<const float4*>(p.window);
         for (int i = tid; i < 16 * 16; i += nt) {

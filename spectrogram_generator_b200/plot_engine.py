@@ -54,6 +54,7 @@ class SpectrogramPath:
 
     # -- the call at PlotEngine.py:113 / :232, with the band mask fused as a crop --
     def _spectrogram_cropped(self, data, fs, nperseg, fmin, fmax):
+        self._last_Sxx_dev = None
         x, out_dtype, is_complex = _prepare_input(data, -1)
         if x.ndim != 1:
             raise ValueError("the reference passes one 1-D sweep per call")
@@ -139,28 +140,41 @@ class SpectrogramPath:
         delta_log_power = np.diff(log_power, prepend=log_power[0])
         return t, np.column_stack([log_power, delta_log_power])
 
+    def _band_ranges(self, bands):
+        """Half-open bin ranges of ``last_f`` selected by the reference's masks ``(f >= low) & (f < high)``
+        (PlotEngine.py:714); ``last_f`` is increasing, so every mask is a contiguous range."""
+        out = []
+        for low, high in bands.values():
+            idx = np.nonzero((self.last_f >= low) & (self.last_f < high))[0]
+            out.append((int(idx[0]), int(idx[-1]) + 1) if idx.size else (0, 0))
+        return out
+
     def calculate_absolute_power(self):
-        """PlotEngine.py:686-690."""
+        """PlotEngine.py:686-690: ``sum(last_Sxx)``, reduced on the device from the spectrogram the last
+        ``_plot_spectrogram`` call left there (``b2s_band_sums_f32``; double accumulators)."""
         if self.last_Sxx is None:
             return None
-        return np.sum(self.last_Sxx)
+        if self._last_Sxx_dev is None or self.last_Sxx.size == 0:
+            return np.sum(self.last_Sxx)
+        # the reference sums the signed values; the kernel clamps at 0 like calculate_band_powers -- a PSD has none
+        return self.last_Sxx.dtype.type(engine().band_sums(self._last_Sxx_dev, [])[-1])
 
     def calculate_band_powers(self, bands=None):
-        """PlotEngine.py:692-719."""
+        """PlotEngine.py:692-719, the sums taken on the device: only ``len(bands) + 1`` numbers are read back."""
         if self.last_Sxx is None or self.last_f is None:
             return None
-        Sxx_linear = np.maximum(0, self.last_Sxx)
         if bands is None:
             bands = DEFAULT_BANDS
-        total_power = np.sum(Sxx_linear)
+        if self._last_Sxx_dev is None or self.last_Sxx.size == 0 or len(bands) > 16:
+            Sxx_linear = np.maximum(0, self.last_Sxx)
+            total_power = np.sum(Sxx_linear)
+            sums = [np.sum(Sxx_linear[(self.last_f >= low) & (self.last_f < high), :]) for low, high in bands.values()]
+        else:
+            res = engine().band_sums(self._last_Sxx_dev, self._band_ranges(bands))
+            sums, total_power = res[:-1], res[-1]
         if total_power < 1e-18:
             return {name: 0.0 for name in bands}
-        power_dict = {}
-        for name, (low, high) in bands.items():
-            mask = (self.last_f >= low) & (self.last_f < high)
-            band_power = np.sum(Sxx_linear[mask, :])
-            power_dict[name] = np.clip(band_power / total_power, 0.0, None)
-        return power_dict
+        return {name: np.clip(band_power / total_power, 0.0, None) for name, band_power in zip(bands, sums)}
 
     def combine(self, sweeps_info, settings):
         """'Combine all sweeps': time concatenation with a segment map

@@ -143,18 +143,9 @@ class Engine:
         if not torch.cuda.is_available():
             raise _lib.B2SError("no CUDA device: the spectrogram engine has no CPU fallback")
 
-    # The kernels fold sqrt(scale/2) into the window taps (|2 X|^2 is then the PSD of an interior bin).
-    # Done on the device that would round every fp32 tap a second time, and at the error level of this
-    # path (rms 2e-6 of a bin 60 dB under a tone) a per-sample relative error of 2^-25 is measurable.
-    # So the fold happens HERE, in float64, with ONE rounding to fp32, and the library is called with
-    # scale = KERNEL_SCALE = 2: its sqrt(scale/2) is then exactly 1.
-    KERNEL_SCALE = 2.0
-
     def window_table(self, plan: Plan, device: torch.device) -> torch.Tensor:
-        """fp32 taps ``w * sqrt(scale/2)`` (folded in float64, rounded once) on ``device``; pass
-        ``KERNEL_SCALE`` as the scale of every library call that uses them."""
         idx = _dev_index(device)
-        key = (plan.window_key, float(plan.scale), idx)
+        key = (plan.window_key, idx)
         with self._lock:
             t = self._windows.pop(key, None)
             if t is None:
@@ -162,8 +153,7 @@ class Engine:
                 # the caching allocator's stream ordering (it was created and is used on this device's streams)
                 while len(self._windows) >= self._MAX_WINDOWS:
                     self._windows.pop(next(iter(self._windows)))
-                taps = (plan.win64 * np.sqrt(0.5 * plan.scale)).astype(np.float32)
-                t = torch.from_numpy(taps).to(torch.device("cuda", idx))
+                t = torch.from_numpy(plan.win64.astype(np.float32)).to(torch.device("cuda", idx))
             self._windows[key] = t                      # (re)insert as most recently used
             return t
 
@@ -199,7 +189,7 @@ class Engine:
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop,
-                    win.data_ptr(), plan.detrend, self.KERNEL_SCALE, int(out_mode), float(db_floor),
+                    win.data_ptr(), plan.detrend, plan.scale, int(out_mode), float(db_floor),
                     int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
                     nframes * kout, stream)
         _lib.check(rc, "b2s_stft_psd")
@@ -240,7 +230,7 @@ class Engine:
         fn = lib.b2s_stft_psd_sum_f32 if x.dtype == torch.float32 else lib.b2s_stft_psd_sum_f64
         with torch.cuda.device(x.device):
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
-                    plan.detrend, self.KERNEL_SCALE, 0, F, out.data_ptr(), F * K, sum_out.data_ptr(), float(post_scale),
+                    plan.detrend, plan.scale, 0, F, out.data_ptr(), F * K, sum_out.data_ptr(), float(post_scale),
                     scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b2s_stft_psd_sum")
         return out, sum_out
@@ -279,7 +269,7 @@ class Engine:
         fn = lib.b2s_stft_band_power_f32 if x.dtype == torch.float32 else lib.b2s_stft_band_power_f64
         with torch.cuda.device(x.device):
             rc = fn(x.data_ptr(), B, n, x.stride(0) if B > 1 else n, plan.nperseg, plan.hop, win.data_ptr(),
-                    plan.detrend, self.KERNEL_SCALE, int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
+                    plan.detrend, plan.scale, int(kmin), int(kmax), int(frame0), int(nframes), out.data_ptr(),
                     nframes, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b2s_stft_band_power")
         return out
@@ -297,6 +287,27 @@ class Engine:
                                            scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "b2s_display_scale_f32")
         return out
+
+    def band_sums(self, s: torch.Tensor, ranges) -> np.ndarray:
+        """Power summaries on the device (PlotEngine.py:686-719): ``s`` is a contiguous CUDA float32
+        ``[frames, bins]`` spectrogram, ``ranges`` up to 16 half-open bin ranges ``(k0, k1)``.  Returns a
+        float64 array of ``len(ranges) + 1`` numbers: ``sum(max(0, s[:, k0:k1]))`` per range, then the
+        total over all bins.  Only these few numbers cross PCIe."""
+        import ctypes
+        lib = _lib.load()
+        if not s.is_cuda or s.dtype != torch.float32 or not s.is_contiguous() or s.dim() != 2 or s.numel() == 0:
+            raise ValueError("band_sums expects a non-empty contiguous CUDA float32 [frames, bins] tensor")
+        ranges = [(int(a), int(b)) for a, b in ranges]
+        nb = len(ranges)
+        k0 = (ctypes.c_int * max(nb, 1))(*[a for a, _ in ranges])
+        k1 = (ctypes.c_int * max(nb, 1))(*[b for _, b in ranges])
+        out = torch.empty(nb + 1, dtype=torch.float64, device=s.device)
+        scratch = torch.empty(int(lib.b2s_band_sums_scratch_elems()), dtype=torch.float64, device=s.device)
+        with torch.cuda.device(s.device):
+            rc = lib.b2s_band_sums_f32(s.data_ptr(), s.shape[0], s.shape[1], k0, k1, nb, out.data_ptr(),
+                                       scratch.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b2s_band_sums_f32")
+        return out.cpu().numpy()
 
     def batch_sum(self, s: torch.Tensor, post_scale: float = 1.0, out: torch.Tensor = None) -> torch.Tensor:
         """Deterministic sum over dim 0 of a contiguous CUDA float32 [B, ...] tensor (optionally

@@ -44,6 +44,42 @@ def test_plot_spectrogram_matches_reference_postprocessing(settings):
         assert abs(bp[k] - bpr[k]) <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["gui_default", "gui_default_log", "wide_band_log", "empty_band"])
+def test_against_the_fixture_the_reference_itself_produced(name):
+    """tests/golden/plot_engine_ref.npz holds what the reference's OWN PlotEngine methods returned
+    (executed from /root/reference/PlotEngine.py by tests/golden/make_plot_engine_golden.py) for float32
+    sweeps on a -70 baseline: last_f / last_t / last_Sxx, the image handed to pcolormesh, the HMM features
+    and the power summaries.  The engine's SpectrogramPath is held to the same bar as everywhere."""
+    from test_reference_plot_engine import load_case
+    g = load_case(name)
+    path = sg.SpectrogramPath()
+    img = path._plot_spectrogram(g["x"], g["fs"], g["settings"])
+    assert np.array_equal(path.last_f, g["last_f"]) and np.array_equal(path.last_t, g["last_t"])
+    assert path.last_Sxx.shape == g["last_Sxx"].shape
+    if not bool(g["has_image"]):
+        assert img is None and path.calculate_absolute_power() == 0
+        return
+    assert_parity(path.last_Sxx, g["last_Sxx"], what=f"{name} last_Sxx")
+    big = g["last_Sxx"] >= 1e-6 * g["last_Sxx"].max()
+    tol = 2e-5 if g["settings"]["log_scale"] else 1e-4
+    assert np.max(np.abs(img - g["image"])[big]) <= tol
+    # power summaries: reduced on the device (b2s_band_sums_f32)
+    np.testing.assert_allclose(path.calculate_absolute_power(), g["absolute_power"], rtol=1e-5)
+    bp = path.calculate_band_powers()
+    assert list(bp.keys()) == [str(s) for s in g["band_names"]]
+    np.testing.assert_allclose([float(v) for v in bp.values()], g["band_powers"], rtol=2e-5, atol=1e-12)
+    # and they equal the host reduction of the copied-back array
+    host = np.maximum(0, path.last_Sxx).astype(np.float64)
+    for (low, high), v in zip(sg.plot_engine.DEFAULT_BANDS.values(), bp.values()):
+        m = (path.last_f >= low) & (path.last_f < high)
+        np.testing.assert_allclose(float(v), host[m].sum() / host.sum(), rtol=1e-12, atol=1e-15)
+    # features (PlotEngine.py:229-242) through the fused band-power epilogue
+    path.last_fs, path.last_settings = g["fs"], g["settings"]
+    t, feat = path._calculate_features(g["x"])
+    assert np.array_equal(t, g["feat_t"]) and feat.shape == g["features"].shape
+    assert np.max(np.abs(feat - g["features"])) <= 1e-4 / np.log(10) * 2
+
+
 def test_empty_band_mask_follows_reference_early_return():
     x, fs = sweep()
     path = sg.SpectrogramPath()

@@ -329,8 +329,9 @@ def test_matches_scipys_own_float32_accuracy():
     """The reference's path fed float32 runs SciPy's float32 pipeline (DUCC r2c in fp32,
     _spectral_py.py:2169).  Measured against the float64 result, the engine's error
     distribution must be no wider than that pipeline's own: RMS and 99.99th-percentile
-    relative error over the above-floor bins within 1.25x (the single worst bin of ~10^6
-    is a noisy statistic, so it only gets a 2x bound).  I.e. the residual is fp32
+    relative error over the above-floor bins within 1.10x / 1.15x (the single worst bin of ~10^6
+    is a noisy statistic -- measured ratios on the full-size configs 0.82 ... 1.26,
+    tests/test_gpu_full_size.py -- so it gets a 1.5x bound).  I.e. the residual is fp32
     rounding, not algorithm."""
     import scipy.signal
     for make in (lambda: synth.config3(n=48000 * 8), lambda: synth.config2(batch=16),
@@ -344,9 +345,9 @@ def test_matches_scipys_own_float32_accuracy():
         big = So >= 1e-6 * So.max()
         ours = np.abs(S.astype(np.float64)[big] - So[big]) / So[big]
         theirs = np.abs(S32.astype(np.float64)[big] - So[big]) / So[big]
-        assert np.sqrt(np.mean(ours ** 2)) <= 1.25 * np.sqrt(np.mean(theirs ** 2))
-        assert np.quantile(ours, 0.9999) <= 1.25 * np.quantile(theirs, 0.9999)
-        assert ours.max() <= 2.0 * theirs.max()
+        assert np.sqrt(np.mean(ours ** 2)) <= 1.10 * np.sqrt(np.mean(theirs ** 2))
+        assert np.quantile(ours, 0.9999) <= 1.15 * np.quantile(theirs, 0.9999)
+        assert ours.max() <= 1.5 * max(theirs.max(), 1e-4)
 
 
 def test_white_noise_floor_statistics():

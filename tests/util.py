@@ -115,10 +115,10 @@ class FullSizeStats:
                              for k, v in rep.items()})
         assert self.abs_ours <= abs_tol, f"{self.what}: abs err {self.abs_ours:.3e} * max"
         assert rep["ours"]["frac_over"] <= tail, f"{self.what}: {rep['ours']['frac_over']:.2e} of the bins miss rel {rel}"
-        bar = 1.25 * max(rel, rep["scipy_f32"]["max"])
+        bar = 1.5 * max(rel, rep["scipy_f32"]["max"])
         assert rep["ours"]["max"] <= bar, f"{self.what}: worst bin {rep['ours']['max']:.3e} > {bar:.3e}"
-        assert rep["ours"]["rms"] <= 1.15 * rep["scipy_f32"]["rms"], f"{self.what}: rms {rep}"
-        assert rep["ours"]["p9999"] <= 1.25 * rep["scipy_f32"]["p9999"], f"{self.what}: p99.99 {rep}"
+        assert rep["ours"]["rms"] <= 1.10 * rep["scipy_f32"]["rms"], f"{self.what}: rms {rep}"
+        assert rep["ours"]["p9999"] <= 1.15 * rep["scipy_f32"]["p9999"], f"{self.what}: p99.99 {rep}"
         return rep
 
 
@@ -153,15 +153,15 @@ class Emulator:
 
     @staticmethod
     def taps(plan, prescale):
-        """(fp32 window table, scale) as the host layer passes them (Engine.window_table: sqrt(scale/2)
-        folded in float64, scale = 2), or -- prescale=False -- raw taps and the true scale, the other
-        form the C ABI accepts."""
+        """(fp32 window table, scale) as the host layer passes them (raw taps, true scale), or --
+        prescale=True -- taps with sqrt(scale/2) folded in float64 and scale = 2, which the kernels
+        take as well (their own fold is then exactly 1; measured: no accuracy gain worth the change)."""
         if prescale:
             return (plan.win64 * np.sqrt(0.5 * plan.scale)).astype(np.float32), 2.0
         return plan.win64.astype(np.float32), plan.scale
 
     def stft_psd(self, x2d, plan, out_mode=0, db_floor=0.0, kmin=0, kmax=None, frame0=0, nframes=None,
-                 grid=2, chunk=0, prescale=True):
+                 grid=2, chunk=0, prescale=False):
         x2d = np.ascontiguousarray(x2d)
         assert x2d.dtype in (np.float32, np.float64) and x2d.ndim == 2
         B, n = x2d.shape
@@ -180,7 +180,7 @@ class Emulator:
         x2d = np.ascontiguousarray(x2d)
         B, n = x2d.shape
         nframes = plan.nframes - frame0 if nframes is None else nframes
-        w, scale = self.taps(plan, True)
+        w, scale = self.taps(plan, False)
         out = np.full((B, nframes), np.nan, np.float32)
         rc = self.lib.emu_stft_psd(x2d.ctypes.data, int(x2d.dtype == np.float64), B, n, n, plan.nperseg,
                                    plan.hop, w.ctypes.data, plan.detrend, scale, 0, 0.0,
@@ -200,7 +200,7 @@ class Emulator:
         x2d = np.ascontiguousarray(x2d)
         B, n = x2d.shape
         F, K = plan.nframes, plan.nbins
-        w, scale = self.taps(plan, True)
+        w, scale = self.taps(plan, False)
         out = np.full((B, F, K), np.nan, np.float32)
         tot = np.full((F, K), np.nan, np.float32)
         c = ctypes
