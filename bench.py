@@ -445,12 +445,13 @@ def run_gpu(args):
     # NCCL kernels spin beside the persistent STFT grids of their peers; reserving SMs for them with
     # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = overlap (default) | peer | sync | async | none.
     # "overlap": the peer kernel on a high-priority side stream, so the all-reduce of step i runs beside the
-    # STFT of step i + 1, in the CTA slots of 5 SMs the STFT grid leaves free (b2s_set_reserved_sms).
+    # STFT of step i + 1, as one-warp CTAs that fit the registers the STFT CTAs leave on every SM.
     mode = os.environ.get("B2S_BENCH_ALLREDUCE", "overlap")
     overlap = (mode == "overlap")
     if overlap:
         mode = "peer"
-    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "5" if (overlap and world > 1) else "0")))
+    # (round 1 reserved 5 SMs for the overlapped reduce; its one-warp CTAs now fit beside the STFT CTAs)
+    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "0")))
     from spectrogram_generator_b200 import _lib
     _lib.load().b2s_set_reserved_sms(reserve)
 

@@ -76,6 +76,15 @@ int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned l
                            int rank, unsigned int epoch, long long elems, float* out, float post_scale,
                            void* stream);
 
+/* The same, with flags: B2S_PEER_CORESIDENT launches the reduce as one-warp CTAs of <= 32 registers, one per
+ * SM, meant to run on a side stream BESIDE the persistent STFT grid of the next step: such a CTA fits the
+ * registers three STFT CTAs leave on an SM, so it never displaces one of them (no b2s_set_reserved_sms
+ * needed).  Same additions in the same order: bit-identical to the plain entry. */
+#define B2S_PEER_CORESIDENT 1
+int b2s_peer_allreduce_ex_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
+                              int rank, unsigned int epoch, long long elems, float* out, float post_scale, int flags,
+                              void* stream);
+
 /* The all-reduce waits for a late peer for B2S_PEER_TIMEOUT_MS (default 120 000) of wall-clock time
  * (%globaltimer), polling with a nanosleep back-off; every rank must therefore enqueue its call
  * within that window.  A kernel whose wait expires does NOT trap: it leaves `out` unwritten and

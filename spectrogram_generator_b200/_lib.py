@@ -94,6 +94,8 @@ SIGNATURES = {
     "b2s_set_option": (c_int, [c_char_p, c_int]),
     "b2s_peer_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_longlong, c_void_p, c_float,
                                        c_void_p]),
+    "b2s_peer_allreduce_ex_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, ctypes.c_uint, c_longlong, c_void_p, c_float,
+                                          c_int, c_void_p]),
     "b2s_peer_allreduce_status": (c_int, [c_void_p]),
     "b2s_last_error": (c_char_p, []),
     "b2s_last_kernel": (c_char_p, []),

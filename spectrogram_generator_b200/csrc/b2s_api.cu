@@ -240,7 +240,7 @@ int launch_pair_impl(const void* kern, const void* kern_mid, const void* kern_wi
     // the shape only decides how many warps share an SM and how many registers each gets.  Measured on B200
     // (tools/microbench.py --set n1024x, profiles/r2_pair_cta_width.md):
     //   128 x 3 CTAs (164 registers)  the default;
-    //   192 x 2 CTAs (168 registers)  hop > 768: three 128-thread CTAs no longer fit their rings there;
+    //   one CTA of 384 (136 registers) hop > 768: three 128-thread CTAs no longer fit their rings there;
     //   one CTA of 480 (128 registers) hop <= 128 and 257..768: 15 warps per SM buy up to 10 %.
     int nt = PP::NT;
     const bool big_launch = a.batch * a.nframes >= 64LL * di.sm_count;
@@ -251,7 +251,7 @@ int launch_pair_impl(const void* kern, const void* kern_mid, const void* kern_wi
     if (env().pair_nt > 0) nt = env().pair_nt / 32 * 32;
     if (nt < 32) nt = 32;
     if (nt > PP::NT_WIDE) nt = PP::NT_WIDE;
-    while (nt > PP::NT_MID && (int)PP::smem_bytes(a.hop, esz, nt) > di.smem_optin) nt -= 32;
+    while (nt > PP::NT && (int)PP::smem_bytes(a.hop, esz, nt) > di.smem_optin) nt -= 32;
     if (nt > PP::NT_MID) kern = kern_wide;
     else if (nt > PP::NT) kern = kern_mid;
     const size_t smem = PP::smem_bytes(a.hop, esz, nt);
@@ -599,6 +599,12 @@ int b2s_stft_psd_sum_f64(const double* x, long long batch, long long n, long lon
 
 int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
                            int rank, unsigned int epoch, long long elems, float* out, float post_scale, void* stream) {
+    return b2s_peer_allreduce_ex_f32(peer_bufs, peer_pads, world, rank, epoch, elems, out, post_scale, 0, stream);
+}
+
+int b2s_peer_allreduce_ex_f32(const unsigned long long* peer_bufs, const unsigned long long* peer_pads, int world,
+                              int rank, unsigned int epoch, long long elems, float* out, float post_scale, int flags,
+                              void* stream) {
     if (!peer_bufs || !peer_pads || !out || world < 1 || world > 16 || rank < 0 || rank >= world || elems < 1)
         return fail(B2S_ERR_BAD_ARG, "b2s_peer_allreduce_f32: bad argument");
     b2s::PeerPtrs pp{};
@@ -624,8 +630,16 @@ int b2s_peer_allreduce_f32(const unsigned long long* peer_bufs, const unsigned l
     rc = peer_err_flag(dev, &err_flag);
     if (rc != B2S_OK) return rc;
     const unsigned long long timeout_ns = (unsigned long long)(env().peer_timeout_ms > 0 ? env().peer_timeout_ms : 120000) * 1000000ULL;
-    b2s::peer_allreduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out, post_scale,
-                                                                         vec_ok, timeout_ns, err_flag);
+    if (flags & B2S_PEER_CORESIDENT) {
+        // one warp per SM: fits the registers three STFT CTAs leave, never displaces one of them
+        long long want32 = (elems / 2 + 31) / 32;
+        const unsigned g32 = (unsigned)(want32 < di.sm_count ? (want32 < 1 ? 1 : want32) : di.sm_count);
+        b2s::peer_allreduce_warp_kernel<<<g32, 32, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out,
+                                                                              post_scale, vec_ok, timeout_ns, err_flag);
+    } else {
+        b2s::peer_allreduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, elems, out,
+                                                                             post_scale, vec_ok, timeout_ns, err_flag);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce_kernel launch");
     return B2S_OK;

@@ -120,6 +120,67 @@ B2S_GLOBAL void peer_allreduce_kernel(const PeerPtrs pp, int world, int rank, un
         out[e] = acc * post_scale;
     }
 }
+
+// The same all-reduce as one-warp CTAs of at most 32 registers per thread, for the launch that runs
+// BESIDE the persistent STFT grid of the next step (PeerMeanReducer(overlap=True)): three 128-thread STFT
+// CTAs of 168 registers leave an SM exactly 1024 registers, i.e. room for one such warp, so these CTAs
+// never take the slot of an STFT CTA -- a displaced STFT CTA starts late, and with the sum-fused
+// kernel's one-round static schedule a late CTA is a late kernel (measured: +6 us on 170).
+// 64-bit peer loads, ranks added in rank order: bit-identical to peer_allreduce_kernel.
+B2S_GLOBAL void __maxnreg__(32) peer_allreduce_warp_kernel(const PeerPtrs pp, int world, int rank, unsigned epoch,
+                                                                  long long elems, float* __restrict__ out,
+                                                                  float post_scale, int vec_ok,
+                                                                  unsigned long long timeout_ns, int* err_flag) {
+    const int lane = (int)threadIdx.x;
+    if (blockIdx.x == 0 && lane < world) {
+        __threadfence_system();
+        unsigned* dst = pp.pad[lane] + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    }
+    int late = 0;
+    if (lane < world) {
+        const unsigned* src = pp.pad[rank] + lane;
+        unsigned v;
+        unsigned ns = 64;
+        const unsigned long long t0 = b2s_globaltimer_ns();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (b2s_globaltimer_ns() - t0 > timeout_ns) {
+                late = 1;
+                atomicExch(err_flag, lane + 1);
+                break;
+            }
+            __nanosleep(ns);
+            if (ns < 2048) ns *= 2;
+        }
+    }
+    if (__any_sync(0xffffffffu, late)) return;
+    const long long tid = (long long)blockIdx.x * 32 + lane;
+    const long long nth = (long long)gridDim.x * 32;
+    const long long n2 = vec_ok ? elems / 2 : 0;
+    for (long long q = tid; q < n2; q += nth) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int r0 = 0; r0 < world; r0 += 4) {          // four ranks' loads in flight, added in rank order
+            float2 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (r0 + j < world) v[j] = __ldcv(reinterpret_cast<const float2*>(pp.buf[r0 + j]) + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (r0 + j < world) {
+                    acc.x += v[j].x;
+                    acc.y += v[j].y;
+                }
+        }
+        reinterpret_cast<float2*>(out)[q] = make_float2(acc.x * post_scale, acc.y * post_scale);
+    }
+    for (long long e = 2 * n2 + tid; e < elems; e += nth) {
+        float acc = 0.f;
+        for (int r = 0; r < world; ++r) acc += __ldcv(pp.buf[r] + e);
+        out[e] = acc * post_scale;
+    }
+}
 #endif
 
 // ---- display scaling (PlotEngine._plot_spectrogram, PlotEngine.py:126-131) -----------------

@@ -238,8 +238,10 @@ class PeerMeanReducer:
                 stream = self.side
             else:
                 stream = cur
-            rc = self._lib.b2s_peer_allreduce_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
-                                                  out.data_ptr(), float(post_scale), stream.cuda_stream)
+            # overlap mode: one-warp CTAs that fit beside the next step's STFT CTAs (B2S_PEER_CORESIDENT)
+            rc = self._lib.b2s_peer_allreduce_ex_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
+                                                     out.data_ptr(), float(post_scale), 1 if self.overlap else 0,
+                                                     stream.cuda_stream)
             _lib.check(rc, "b2s_peer_allreduce_f32")
             if self.overlap:
                 if not caller_out:
