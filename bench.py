@@ -445,13 +445,12 @@ def run_gpu(args):
     # NCCL kernels spin beside the persistent STFT grids of their peers; reserving SMs for them with
     # b2s_set_reserved_sms(8) only brings it back to 0.63): B2S_BENCH_ALLREDUCE = overlap (default) | peer | sync | async | none.
     # "overlap": the peer kernel on a high-priority side stream, so the all-reduce of step i runs beside the
-    # STFT of step i + 1, as one-warp CTAs that fit the registers the STFT CTAs leave on every SM.
+    # STFT of step i + 1, in the CTA slots of 5 SMs the STFT grid leaves free (b2s_set_reserved_sms).
     mode = os.environ.get("B2S_BENCH_ALLREDUCE", "overlap")
     overlap = (mode == "overlap")
     if overlap:
         mode = "peer"
-    # (round 1 reserved 5 SMs for the overlapped reduce; its one-warp CTAs now fit beside the STFT CTAs)
-    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "0")))
+    reserve = max(0, int(os.environ.get("B2S_BENCH_RESERVE_SMS", "5" if (overlap and world > 1) else "0")))
     from spectrogram_generator_b200 import _lib
     _lib.load().b2s_set_reserved_sms(reserve)
 
@@ -468,7 +467,8 @@ def run_gpu(args):
     if world > 1 and mode == "peer":
         try:
             from spectrogram_generator_b200.distributed import PeerMeanReducer
-            peer = PeerMeanReducer(plan.nframes * plan.nbins, dev, overlap=overlap)
+            peer = PeerMeanReducer(plan.nframes * plan.nbins, dev, overlap=overlap,
+                                   coresident=os.environ.get("B2S_BENCH_PEER_CORESIDENT", "0") == "1")
         except Exception as e:          # pragma: no cover
             if rank == 0:
                 print(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)

@@ -167,7 +167,7 @@ class PeerMeanReducer:
     then ``mean = r.reduce(1.0 / total_sweeps)``.
     """
 
-    def __init__(self, elems: int, device, group=None, overlap: bool = False):
+    def __init__(self, elems: int, device, group=None, overlap: bool = False, coresident: bool = False):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -183,6 +183,11 @@ class PeerMeanReducer:
         # slot e % 3 is rewritten for epoch e + 3 after this rank's reduce(e + 1) has completed, which
         # it only does once every peer has announced e + 1, i.e. has finished reading epoch e.
         self.overlap = bool(overlap)
+        # coresident: launch the reduce as one-warp CTAs (B2S_PEER_CORESIDENT) instead of a few 256-thread CTAs in
+        # reserved slots.  Measured on 2 x B200 beside the 168-register STFT CTAs: registers are handed out to
+        # four warps at a time, so even a one-warp CTA does not fit the 1024 registers three STFT CTAs leave and
+        # displaces one of them on every SM (0.176 -> 0.194 ms per step).  Off by default.
+        self.coresident = bool(coresident)
         self.nbuf = 3 if self.overlap else 2
         self.stride = (self.elems + 3) // 4 * 4           # every slot 16-byte aligned: 128-bit peer loads
         self.buf = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
@@ -238,9 +243,8 @@ class PeerMeanReducer:
                 stream = self.side
             else:
                 stream = cur
-            # overlap mode: one-warp CTAs that fit beside the next step's STFT CTAs (B2S_PEER_CORESIDENT)
             rc = self._lib.b2s_peer_allreduce_ex_f32(bufs, self._pads, self.world, self.rank, self.epoch, self.elems,
-                                                     out.data_ptr(), float(post_scale), 1 if self.overlap else 0,
+                                                     out.data_ptr(), float(post_scale), 1 if self.coresident else 0,
                                                      stream.cuda_stream)
             _lib.check(rc, "b2s_peer_allreduce_f32")
             if self.overlap:
