@@ -145,7 +145,7 @@ bool stream_capturing(cudaStream_t stream) {
 // diagnostic switches, read once per process
 struct EnvSwitches {
     bool allow_duo = true, duo1024 = true, allow_duo4 = true, allow_big = true, dynamic_units = true;
-    bool allow_pair = true, fused_sum = true, sum_acc_smem = false;
+    bool allow_pair = true, allow_pairq = true, fused_sum = true, sum_acc_smem = false;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
     int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
     int peer_timeout_ms = 0;     // B2S_PEER_TIMEOUT_MS: how long the peer all-reduce waits for a late rank (0: 120 s)
@@ -158,6 +158,7 @@ struct EnvSwitches {
         allow_big = !on("B2S_NO_BIG");
         dynamic_units = !on("B2S_STATIC_UNITS");
         allow_pair = !on("B2S_NO_PAIR");
+        allow_pairq = !on("B2S_NO_PAIRQ");
         fused_sum = !on("B2S_NO_FUSED_SUM");
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
@@ -296,6 +297,56 @@ int launch_pair_impl(const void* kern, const void* kern_mid, const void* kern_wi
     return B2S_OK;
 }
 
+// the staged-sample kernel for nperseg >= 2048: one CTA per SM, as many frame groups as its shared memory holds
+int launch_pairq_impl(const void* kern, int group_threads, int nt_max, size_t (*smem_fn)(int, int), int esz,
+                      const b2s::PairQConst& qc, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    int nt = nt_max / group_threads * group_threads;
+    if (env().pair_nt > 0) nt = env().pair_nt / group_threads * group_threads;
+    if (nt < group_threads) nt = group_threads;
+    if (nt > nt_max) nt = nt_max / group_threads * group_threads;
+    while (nt > group_threads && (long long)smem_fn(esz, nt) > di.smem_optin) nt -= group_threads;
+    const size_t smem = smem_fn(esz, nt);
+    if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this nperseg");
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        PairState& ks = g_pair[std::make_pair(kern, ((long long)dev << 40) | ((long long)nt << 24) | (long long)smem)];
+        if (ks.occ == 0) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            ks.occ = 1;
+        }
+    }
+    const int fpc = nt / group_threads;
+    const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
+    const long long resident_ctas = (long long)(di.sm_count - reserve);
+    const long long resident_groups = resident_ctas * fpc;
+    b2s::StftParams p{};
+    std::string err;
+    dynamic = dynamic && (a.batch * a.nframes >= 8 * resident_groups) && !stream_capturing(stream);
+    rc = b2s::plan_stft(a, fpc, resident_groups, p, err, dynamic);
+    if (rc < 0) return fail(rc, err);
+    if (p.n_units == 0) return B2S_OK;
+    b2s::plan_pair_units(a, resident_groups, env().pair_units, dynamic, p);
+    p.ring = a.nperseg;
+    if (dynamic) {
+        rc = work_counters(dev, stream, &p.work);
+        if (rc != B2S_OK) return rc;
+    }
+    rc = twiddles(dev, a.nperseg, false, &p.tw);
+    if (rc != B2S_OK) return rc;
+    const long long need = (p.n_units + fpc - 1) / fpc;
+    const long long grid = (need < resident_ctas) ? need : resident_ctas;
+    b2s::PairQConst qcc = qc;
+    void* args[] = {&p, &qcc};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)nt), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "pairq stft kernel launch");
+    return B2S_OK;
+}
+
 // direct-DFT family: one CTA per frame, grid-stride
 template <typename Tin>
 int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
@@ -354,6 +405,7 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
     L.allow_big = sw.allow_big;
     L.dynamic_units = sw.dynamic_units;
     L.allow_pair = sw.allow_pair && sw.allow_duo;
+    L.allow_pairq = sw.allow_pairq && sw.allow_duo;
     // the reference's call (linear power, every bin) takes the branch-free epilogue
     const bool general = (a.out_mode != B2S_OUT_LINEAR) || a.kmin != 0 || a.kmax != a.nperseg / 2;
     const int mode = a.band_mode ? b2s::EPI_BAND : (general ? b2s::EPI_GENERAL : b2s::EPI_PLAIN);
@@ -463,6 +515,11 @@ int b2s_launch_any(const void* kern, int nt, size_t smem, int fpc, const b2s::St
     return launch_any_impl(kern, nt, smem, fpc, a, stream, false, dynamic);
 }
 
+int b2s_launch_pairq(const void* kern, int group_threads, int nt_max, size_t (*smem_fn)(int, int), int esz,
+                     const b2s::PairQConst& qc, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic) {
+    return launch_pairq_impl(kern, group_threads, nt_max, smem_fn, esz, qc, a, stream, dynamic);
+}
+
 int b2s_launch_pair(const void* kern, const void* kern_mid, const void* kern_wide, int esz, const b2s::StftArgs& a,
                     cudaStream_t stream, bool dynamic) {
     return launch_pair_impl(kern, kern_mid, kern_wide, esz, a, stream, dynamic);
@@ -493,6 +550,7 @@ int b2s_set_option(const char* name, int value) {
     else if (n == "no_big") e.allow_big = !on;
     else if (n == "static_units") e.dynamic_units = !on;
     else if (n == "no_pair") e.allow_pair = !on;
+    else if (n == "no_pairq") e.allow_pairq = !on;
     else if (n == "no_fused_sum") e.fused_sum = !on;
     else if (n == "sum_acc_smem") e.sum_acc_smem = on;
     else if (n == "pair_units") e.pair_units = value;

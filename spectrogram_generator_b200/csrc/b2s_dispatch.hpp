@@ -34,6 +34,7 @@
 #include "b2s_duo_cta_kernel.cuh"
 #include "b2s_duo_kernel.cuh"
 #include "b2s_pair_kernel.cuh"
+#include "b2s_pairq_kernel.cuh"
 #include "b2s_warp_kernel.cuh"
 
 namespace b2s {
@@ -134,6 +135,13 @@ int dispatch_duo_big(const StftArgs& a, Launcher& L) {
     return L.template duo_cta<LOG2N, Tin, MODE>(a);
 }
 
+// staged-sample kernel for nperseg 2048 .. 16384 (b2s_pairq_kernel.cuh): 16-byte aligned frames
+template <class Launcher>
+bool pairq_ok(const StftArgs& a, const Launcher& L) {
+    return L.allow_pairq && pairq_kernel_ok(a.x, a.batch, a.x_batch_stride, a.nperseg, a.hop) &&
+           reinterpret_cast<uintptr_t>(a.window) % 16 == 0;
+}
+
 template <typename Tin, int MODE, class Launcher>
 int dispatch_tg(const StftArgs& a, Launcher& L) {
     const int log2n = ilog2_exact(a.nperseg);
@@ -151,10 +159,18 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
                 return L.template pair<10, Tin, MODE>(a);
             if (L.allow_duo && L.duo1024) return dispatch_duo_big<10, Tin, MODE>(a, L);
             return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
-        case 11: return L.allow_duo ? dispatch_duo_big<11, Tin, MODE>(a, L) : L.template cta<11, Tin, MODE>(a);
-        case 12: return L.allow_duo ? dispatch_duo_big<12, Tin, MODE>(a, L) : L.template cta<12, Tin, MODE>(a);
-        case 13: return L.allow_big ? L.template big<13, Tin, MODE>(a) : L.template cta<13, Tin, MODE>(a);
-        case 14: return L.allow_big ? L.template big<14, Tin, MODE>(a) : L.template cta<14, Tin, MODE>(a);
+        case 11:
+            if (pairq_ok(a, L)) return L.template pairq<11, Tin, MODE>(a);
+            return L.allow_duo ? dispatch_duo_big<11, Tin, MODE>(a, L) : L.template cta<11, Tin, MODE>(a);
+        case 12:
+            if (pairq_ok(a, L)) return L.template pairq<12, Tin, MODE>(a);
+            return L.allow_duo ? dispatch_duo_big<12, Tin, MODE>(a, L) : L.template cta<12, Tin, MODE>(a);
+        case 13:
+            if (pairq_ok(a, L)) return L.template pairq<13, Tin, MODE>(a);
+            return L.allow_big ? L.template big<13, Tin, MODE>(a) : L.template cta<13, Tin, MODE>(a);
+        case 14:
+            if (pairq_ok(a, L)) return L.template pairq<14, Tin, MODE>(a);
+            return L.allow_big ? L.template big<14, Tin, MODE>(a) : L.template cta<14, Tin, MODE>(a);
         default: return B2S_ERR_UNSUPPORTED;
     }
 }

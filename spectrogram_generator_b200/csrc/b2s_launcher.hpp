@@ -20,6 +20,10 @@ int b2s_launch_pair(const void* kern, const void* kern_mid, const void* kern_wid
 // Records which kernel the calling thread launched last (b2s_last_kernel() in include/b2s.h).
 void b2s_note_kernel(const char* family, const b2s::StftArgs& a);
 
+// One launch of the staged-sample kernel for nperseg >= 2048 (b2s_pairq_kernel.cuh).  Defined in b2s_api.cu.
+int b2s_launch_pairq(const void* kern, int group_threads, int nt_max, size_t (*smem_fn)(int, int), int esz,
+                     const b2s::PairQConst& qc, const b2s::StftArgs& a, cudaStream_t stream, bool dynamic);
+
 namespace b2s {
 
 struct CudaLauncher {
@@ -29,6 +33,16 @@ struct CudaLauncher {
     bool allow_duo4 = true;
     bool allow_big = true;
     bool allow_pair = true;
+    bool allow_pairq = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int pairq(const StftArgs& a) {
+        using PP = PairQPlan<LOG2N>;
+        b2s_note_kernel("stft_psd_pairq_kernel (staged samples: TMA ring, sub-sequence pairs in fp32x2, fused untangle + radix-Q)", a);
+        PairQConst qc;
+        make_pairq_const<PP::HW>(qc);
+        return b2s_launch_pairq((const void*)stft_psd_pairq_kernel<LOG2N, Tin, MODE>, PP::G, PP::NT_MAX, &PP::smem_bytes,
+                                (int)sizeof(Tin), qc, a, stream, dynamic_units);
+    }
     template <int LOG2N, typename Tin, int MODE>
     int pair(const StftArgs& a) {
         b2s_note_kernel("stft_psd_pair_kernel (staged samples: TMA ring, sub-sequence pairs in fp32x2)", a);

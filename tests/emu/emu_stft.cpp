@@ -19,7 +19,7 @@ using namespace b2s;
 // which kernel family the last emu_stft_psd call ran (tests assert that a shape reaches the kernel it is meant for)
 static int g_last_family = 0;
 extern "C" int emu_last_family() { return g_last_family; }
-enum { FAM_PAIR = 9, FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
+enum { FAM_PAIRQ = 10, FAM_PAIR = 9, FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
 
 struct EmuLauncher {
     StftParams p;
@@ -32,6 +32,21 @@ struct EmuLauncher {
     bool dynamic_units = true;
     int work[2] = {0, 0};
     const StftArgs* args = nullptr;
+    bool allow_pairq = true;
+    template <int LOG2N, typename Tin, int MODE>
+    int pairq(const StftArgs& a) {
+        g_last_family = FAM_PAIRQ;
+        using PP = PairQPlan<LOG2N>;
+        StftParams q = p;
+        if (dynamic_units) q.work = work;
+        q.ring = PP::N;
+        const int nt = (PP::G <= 128) ? (PP::NT_MAX / PP::G >= 2 ? 2 * PP::G : PP::G) : PP::G;     // two groups per CTA where they fit
+        if (pair_units >= 0) plan_pair_units(a, (long long)grid * (nt / PP::G), pair_units, dynamic_units, q);
+        PairQConst qc;
+        make_pairq_const<PP::HW>(qc);
+        emu::launch(grid, nt, PP::smem_bytes((int)sizeof(Tin), nt), [&] { stft_psd_pairq_kernel<LOG2N, Tin, MODE>(q, qc); });
+        return (work[0] == 0 && work[1] == 0) ? 0 : -100;
+    }
     template <int LOG2N, typename Tin, int MODE>
     int pair(const StftArgs& a) {
         g_last_family = FAM_PAIR;
@@ -151,6 +166,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
     if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
     if (const char* v = getenv("B2S_NO_PAIR")) L.allow_pair = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_NO_PAIRQ")) L.allow_pairq = (atoi(v) == 0);
     if (const char* v = getenv("B2S_PAIR_UNITS")) L.pair_units = atoi(v);
     if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     return dispatch_stft(a, L);

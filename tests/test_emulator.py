@@ -288,19 +288,19 @@ def test_frame_duo_cta_kernel(emu, nperseg, hop, detrend):
 
 
 @pytest.mark.parametrize("nperseg,hop", [(1024, 256), (1024, 128), (1024, 512), (1024, 896), (1024, 1024),
-                                         (2048, 512), (2048, 1024), (4096, 1024), (4096, 512)])
+                                         (2048, 512), (2048, 1024), (4096, 1024), (4096, 512),
+                                         (8192, 2048), (16384, 4096)])
 @pytest.mark.parametrize("detrend", ["constant", False])
 @pytest.mark.parametrize("pair", [True, False])
 def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     """nperseg 1024 / 2048 / 4096 with hop = S * nperseg/16 run on the four-step duo kernel
     (256-point sub-transforms per half-warp + fused radix-R final stage): odd frame counts, runs
     cut at odd lengths, crop / frame range / band power, float64 samples; chunking-invariant.
-    nperseg 1024 on 16-byte aligned rows goes to the staged-sample pair kernel (b2s_pair_kernel.cuh)
-    unless B2S_NO_PAIR=1; both are held to the same checks."""
+    On 16-byte aligned rows these shapes go to the staged-sample kernels (b2s_pair_kernel.cuh for 1024,
+    b2s_pairq_kernel.cuh above) unless B2S_NO_PAIR=1 / B2S_NO_PAIRQ=1; both are held to the same checks."""
     if not pair:
-        if nperseg != 1024:
-            pytest.skip("the pair kernel only takes nperseg 1024")
         monkeypatch.setenv("B2S_NO_PAIR", "1")
+        monkeypatch.setenv("B2S_NO_PAIRQ", "1")
     nfr = 5
     n = nperseg + hop * (nfr - 1) + 4          # even rows: the packed kernels need 8-byte aligned frames
     x = signal(2, n, nperseg + hop + 1, dc=-3.0 if detrend else 0.0)
@@ -310,7 +310,8 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
     So = np.moveaxis(So, -1, -2)
     a = emu.stft_psd(x, plan, chunk=3, grid=1)
-    assert emu.last_family() == ("pair" if (pair and nperseg == 1024) else "duo4")
+    assert emu.last_family() == (("pair" if nperseg == 1024 else "pairq") if pair else
+                                 ("duo4" if nperseg <= 4096 else "big"))
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"{emu.last_family()} {nperseg}/{hop}")
     assert np.array_equal(a, b)

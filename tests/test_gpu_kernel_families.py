@@ -117,6 +117,55 @@ def test_staged_sample_pair_kernel(hop, detrend):
     assert_parity(other.cpu().numpy(), So, what=f"duo 1024/{hop}")
 
 
+@pytest.mark.parametrize("nperseg,hop", [(2048, 512), (2048, 1792), (2048, 36), (4096, 1024), (4096, 4096),
+                                         (8192, 2048), (8192, 1000), (16384, 4096), (16384, 14336)])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_staged_sample_kernel_2048_to_16384(nperseg, hop, detrend):
+    """b2s_pairq_kernel.cuh (TMA ring per frame group, Q = nperseg/256 real sub-sequences in packed pairs,
+    fused untangle + radix-Q final stage): parity, bit-identity across run lengths / schedules / float64
+    samples / frame ranges and crops, with the round-1 kernels as a second opinion."""
+    from spectrogram_generator_b200 import _lib
+    rng = np.random.default_rng(nperseg + hop)
+    B, nfr = 2, 11
+    n = (nperseg + hop * (nfr - 1) + 5 + 3) // 4 * 4
+    x = _signal(rng, B, n, dc=-70.0 if detrend else 0.0)
+    kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = sg.triage(n, 20000.0, kw["window"], nperseg, nperseg - hop, None, detrend, True, "density", "psd")
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    eng = sg.engine()
+    xd = torch.from_numpy(x).cuda()
+    full = eng.stft_psd(xd, plan)
+    assert "pairq" in _lib.last_kernel()
+    assert_parity(full.cpu().numpy(), So, what=f"pairq {nperseg}/{hop}")
+    try:
+        for units in (1, 3, 50):
+            _lib.set_option("pair_units", units)
+            assert torch.equal(eng.stft_psd(xd, plan), full)
+        _lib.set_option("static_units", 1)
+        assert torch.equal(eng.stft_psd(xd, plan), full)
+    finally:
+        _lib.set_option("pair_units", 0)
+        _lib.set_option("static_units", 0)
+    assert torch.equal(eng.stft_psd(xd.double(), plan), full)
+    K = nperseg // 2
+    part = eng.stft_psd(xd, plan, kmin=7, kmax=K - 9, frame0=3, nframes=nfr - 5)
+    assert torch.equal(part, full[:, 3:nfr - 2, 7:K - 8])
+    band = eng.band_power(xd, plan, 7, K - 9).cpu().numpy()
+    np.testing.assert_allclose(band, full[:, :, 7:K - 8].double().sum(dim=-1).cpu().numpy(), rtol=3e-6)
+    db = eng.stft_psd(xd, plan, out_mode=1, db_floor=float(1e-6 * So.max())).cpu().numpy()
+    big = So >= 1e-6 * So.max()
+    assert np.max(np.abs(db - 10 * np.log10(np.maximum(So, 1e-6 * So.max())))[big]) <= 1e-3
+    _lib.set_option("no_pairq", 1)
+    try:
+        other = eng.stft_psd(xd, plan)
+        assert "pairq" not in _lib.last_kernel()
+    finally:
+        _lib.set_option("no_pairq", 0)
+    assert_parity(other.cpu().numpy(), So, what=f"round-1 kernel {nperseg}/{hop}")
+
+
 def test_float64_samples_on_a_large_dc_level_keep_their_signal():
     """float64 input (neo / NIX sweeps, SweepManager.py:135-136): the pair kernel subtracts the frame's
     pivot in double before the cast, so a 1e-3 signal on a DC level of 1e4 -- which float32 samples
