@@ -145,7 +145,7 @@ bool stream_capturing(cudaStream_t stream) {
 // diagnostic switches, read once per process
 struct EnvSwitches {
     bool allow_duo = true, duo1024 = true, allow_duo4 = true, allow_big = true, dynamic_units = true;
-    bool allow_pair = true, allow_pairq = true, fused_sum = true, sum_acc_smem = false;
+    bool allow_pair = true, allow_pairq = false, fused_sum = true, sum_acc_smem = false;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
     int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
     int peer_timeout_ms = 0;     // B2S_PEER_TIMEOUT_MS: how long the peer all-reduce waits for a late rank (0: 120 s)
@@ -158,7 +158,9 @@ struct EnvSwitches {
         allow_big = !on("B2S_NO_BIG");
         dynamic_units = !on("B2S_STATIC_UNITS");
         allow_pair = !on("B2S_NO_PAIR");
-        allow_pairq = !on("B2S_NO_PAIRQ");
+        // the staged-sample kernel for nperseg >= 2048 is correct but measured slower than the round-1 kernels
+        // (profiles/r2_pairq_vs_round1.md): opt-in
+        allow_pairq = on("B2S_PAIRQ");
         fused_sum = !on("B2S_NO_FUSED_SUM");
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);

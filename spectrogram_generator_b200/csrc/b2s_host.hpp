@@ -60,16 +60,15 @@ inline void make_tables_t(std::vector<float>& out) {
         for (int k = 0; k < PL::NS; ++k) put_w(out, PL::OFF_FIN + (r - 1) * PL::NS + k, (long long)r * k, PL::M);
     for (int k = 0; k <= PL::M; ++k) put_w(out, PL::OFF_POST + k, k, PL::N);
     if constexpr (LOG2N >= 11) {
-        // per-kappa twiddle pairs of the staged-sample kernel (b2s_pairq_kernel.cuh): for kap = 0 .. 128 and
-        // half-warp sp, two float4 (wr[4sp], wr[4sp+1], wi[4sp], wi[4sp+1]) and the same for 4sp+2, 4sp+3,
-        // w[r] = W_N^(r kap)
+        // twiddle pairs of the staged-sample kernel (b2s_pairq_kernel.cuh), [2 sp + v][kap] float4 with
+        // kap = 0 .. 128: (wr[r], wr[r+1], wi[r], wi[r+1]) for r = 4 sp + 2 v, w[r] = W_N^(r kap)
         constexpr int HW = PL::N / 1024;
         constexpr int OFF_PQ = PL::TABLE + (PL::TABLE & 1);
         out.resize(2 * (size_t)(OFF_PQ + 129 * 4 * HW), 0.f);
         for (int kap = 0; kap <= 128; ++kap)
             for (int sp = 0; sp < HW; ++sp)
                 for (int v = 0; v < 2; ++v) {
-                    float* q = out.data() + 2 * (size_t)OFF_PQ + 4 * ((size_t)kap * 2 * HW + 2 * sp + v);
+                    float* q = out.data() + 2 * (size_t)OFF_PQ + 4 * ((size_t)(2 * sp + v) * 129 + kap);
                     for (int h = 0; h < 2; ++h) {
                         const long long r = 4 * sp + 2 * v + h;
                         const double a = 2.0 * M_PI * (double)((r * kap) % PL::N) / (double)PL::N;

@@ -390,11 +390,6 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
                     }
                 }
             }
-            // every lane has read its samples: the ring positions before frame 2 (it + 1) are free
-            __syncwarp();
-            if (it + 1 < nit) issue(un, it + 1);
-            else if (have_next) issue(unn, 0);
-
             if (p.detrend) {
                 // mean of the residual, removed inside the window multiply
                 float2 sr[16];
@@ -424,6 +419,13 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
                     v[i].im = pk_mul(v[i].im, cmk(w.z, w.w));
                 }
             }
+
+            // Every lane has CONSUMED its samples (a barrier alone does not wait for shared-memory loads still in
+            // flight): the ring positions before frame 2 (it + 1) are free -- feed the next pair's samples, or the
+            // next run's first pair, into them.
+            __syncwarp();
+            if (it + 1 < nit) issue(un, it + 1);
+            else if (have_next) issue(unn, 0);
 
             // ---- sub-transforms: radix-16, 16 x 16 transpose inside the half-warp, radix-16 ----
             c2radix16(v);

@@ -61,7 +61,7 @@ struct PairQPlan {
     static size_t smem_bytes(int esz, int nt) {
         return (size_t)off_ring(nt) * sizeof(float4) + (size_t)(nt / G) * ring_samples() * esz;
     }
-    // per-kappa twiddle table behind Plan::TABLE (float2 units): 129 x 2 HW float4
+    // twiddle table behind Plan::TABLE (float2 units): [2 HW][129] float4
     static constexpr int OFF_PQ = PL::TABLE + (PL::TABLE & 1);           // 16-byte aligned
     static constexpr int TABLE_PQ = OFF_PQ + 129 * 4 * HW;
 };
@@ -115,10 +115,16 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
     const int ngroups = nt / G;
     const int grp = tid / G;
     const int j = tid - grp * G;                         // thread inside the frame's group
-    const int sp = j >> 4;                               // half-warp: sub-sequences 4 sp .. 4 sp + 3
+    // Half-warp sp owns sub-sequences 4 sp .. 4 sp + 3.  (A shared-memory LDS.128 is served a quarter-warp at a
+    // time and the words of a quarter are HW apart on the linear ring: 2-way bank conflicts on the sample and
+    // window loads at HW = 2, 4-way above -- measured 25 % / 55 % of the shared wavefronts,
+    // profiles/r2_pairq_*.ncu_summary.txt.  Interleaving the two sub-transforms of a warp removes them for
+    // HW = 2 but moves the conflicts to the transposes; a conflict-free layout needs the ring stored
+    // sub-sequence-major, i.e. 16-byte cp.async copies instead of one bulk copy.  See DESIGN.md.)
+    const int sp = j >> 4;
     const int t = j & 15;
     const int lane = tid & 31;
-    float4* const buf = sm4 + PP::OFF_BUF + (tid >> 4) * PP::BUF;                 // this half-warp's
+    float4* const buf = sm4 + PP::OFF_BUF + (grp * HW + sp) * PP::BUF;            // this sub-transform's
     float4* const xb = sm4 + PP::OFF_BUF + (grp * HW) * PP::BUF;                  // the group's HW buffers
     float* const red = reinterpret_cast<float*>(sm4 + PP::off_red(nt) + grp * PP::red_f4());
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::off_bar(nt) + grp);
@@ -299,7 +305,6 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
 #pragma unroll
                         for (int i = 0; i < w; ++i) s[i] += s[i + w];
                     c = group_sum(s[0], 0) * (1.0f / (float)N);
-                    if constexpr (WG > 1) need_sync = false;          // group_sum's barrier came after every thread's reads
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         v[i].re = pk_add(cmk(raw[i].x, raw[i].y), cmk(-c, -c));
@@ -313,11 +318,6 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                     }
                 }
             }
-            // every thread of the group has read its samples: the first `hop` positions of this frame are free
-            if (need_sync) gsync();
-            if (it + 1 < un.nf) issue(un, it + 1);
-            else if (have_next) issue(unn, 0);
-
             auto taps = [&](int i) -> float4 {
                 const int wi = sp + HW * (t + 16 * i);
                 if constexpr (PP::WIN_SMEM) {
@@ -336,6 +336,7 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
 #pragma unroll
                     for (int i = 0; i < w; ++i) sr[i] = pk_add(sr[i], sr[i + w]);
                 const float nr = group_sum(sr[0].x + sr[0].y, 1) * (-1.0f / (float)N);
+                if constexpr (WG > 1) need_sync = false;  // that sum's barrier came after every thread had consumed its samples
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float4 w = taps(i);
@@ -350,6 +351,13 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                     v[i].im = pk_mul(v[i].im, cmk(w.z, w.w));
                 }
             }
+            // Every thread of the group has CONSUMED its samples (a barrier alone does not wait for shared-memory
+            // loads that are still in flight -- measured: frames built from half-overwritten samples when the copy
+            // below was issued right after the loads): the first `hop` positions of this frame are free, feed
+            // the next frame's samples (or the next run's first frame) into them.
+            if (need_sync) gsync();
+            if (it + 1 < un.nf) issue(un, it + 1);
+            else if (have_next) issue(unn, 0);
 
             // ---- sub-transforms: radix-16, 16 x 16 transpose inside the half-warp, radix-16 ----
             c2radix16(v);
@@ -386,14 +394,14 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
             auto task = [&](int kap, bool dc, bool mid) {
                 const int kapm = (256 - kap) & 255;
                 cpx2 U[HW], V[HW];
-                const float4* const tw = pq + (size_t)kap * (2 * HW);
+                const float4* const tw = pq + kap;         // [2 HW][129]: consecutive lanes read consecutive entries
 #pragma unroll
                 for (int s = 0; s < HW; ++s) {
                     const float4 f4 = xb[s * PP::BUF + kap], g4 = xb[s * PP::BUF + kapm];
                     const cpx2 F{cmk(f4.x, f4.y), cmk(f4.z, f4.w)}, Gm{cmk(g4.x, g4.y), cmk(g4.z, g4.w)};
                     const cpx2 u{pk_add(F.re, Gm.re), pk_sub(F.im, Gm.im)};       // (2 X_4s, 2 X_4s+1) = F + conj(F')
                     const cpx2 w{pk_add(F.im, Gm.im), pk_sub(Gm.re, F.re)};       // (2 X_4s+2, 2 X_4s+3) = -i (F - conj(F'))
-                    const float4 tu = __ldg(tw + 2 * s), tv = __ldg(tw + 2 * s + 1);
+                    const float4 tu = __ldg(tw + (2 * s) * 129), tv = __ldg(tw + (2 * s + 1) * 129);
                     U[s] = c2mul_vec(u, cmk(tu.x, tu.y), cmk(tu.z, tu.w));        // Y_r = W_N^(r kap) 2 X_r
                     V[s] = c2mul_vec(w, cmk(tv.x, tv.y), cmk(tv.z, tv.w));
                 }

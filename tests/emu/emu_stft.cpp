@@ -32,7 +32,7 @@ struct EmuLauncher {
     bool dynamic_units = true;
     int work[2] = {0, 0};
     const StftArgs* args = nullptr;
-    bool allow_pairq = true;
+    bool allow_pairq = false;        // opt-in (B2S_PAIRQ=1), as in the library
     template <int LOG2N, typename Tin, int MODE>
     int pairq(const StftArgs& a) {
         g_last_family = FAM_PAIRQ;
@@ -166,7 +166,7 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
     if (const char* v = getenv("B2S_NO_DUO4")) L.allow_duo4 = (atoi(v) == 0);
     if (const char* v = getenv("B2S_NO_BIG")) L.allow_big = (atoi(v) == 0);
     if (const char* v = getenv("B2S_NO_PAIR")) L.allow_pair = (atoi(v) == 0);
-    if (const char* v = getenv("B2S_NO_PAIRQ")) L.allow_pairq = (atoi(v) == 0);
+    if (const char* v = getenv("B2S_PAIRQ")) L.allow_pairq = (atoi(v) != 0);
     if (const char* v = getenv("B2S_PAIR_UNITS")) L.pair_units = atoi(v);
     if (const char* v = getenv("B2S_STATIC_UNITS")) L.dynamic_units = (atoi(v) == 0);
     return dispatch_stft(a, L);

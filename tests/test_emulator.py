@@ -297,10 +297,12 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     (256-point sub-transforms per half-warp + fused radix-R final stage): odd frame counts, runs
     cut at odd lengths, crop / frame range / band power, float64 samples; chunking-invariant.
     On 16-byte aligned rows these shapes go to the staged-sample kernels (b2s_pair_kernel.cuh for 1024,
-    b2s_pairq_kernel.cuh above) unless B2S_NO_PAIR=1 / B2S_NO_PAIRQ=1; both are held to the same checks."""
+    b2s_pairq_kernel.cuh above, the latter opt-in with B2S_PAIRQ=1) unless B2S_NO_PAIR=1; all are held to the
+    same checks."""
     if not pair:
         monkeypatch.setenv("B2S_NO_PAIR", "1")
-        monkeypatch.setenv("B2S_NO_PAIRQ", "1")
+    else:
+        monkeypatch.setenv("B2S_PAIRQ", "1")            # nperseg >= 2048: the staged-sample kernel is opt-in
     nfr = 5
     n = nperseg + hop * (nfr - 1) + 4          # even rows: the packed kernels need 8-byte aligned frames
     x = signal(2, n, nperseg + hop + 1, dc=-3.0 if detrend else 0.0)

@@ -77,6 +77,10 @@ def main():
     if args.set == "n1024ref":      # nperseg 1024 at the reference's default overlap and without overlap
         shapes += [(1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 1024, 896),
                    (1000, 40960, 1024, 1024)]
+    if args.set == "n2048":
+        shapes += [(1024, 100_000, 2048, 512)]
+    if args.set == "n8192":
+        shapes += [(1024, 100_000, 8192, 2048)]
     if args.set == "n1024x":        # nperseg 1024 over hops and batch shapes (B2S_NO_PAIR=1: the four-step duo / CTA kernels)
         for hop in (128, 256, 512, 896, 1024):
             shapes += [(1000, 40000, 1024, hop), (1024, 100_000, 1024, hop)]
