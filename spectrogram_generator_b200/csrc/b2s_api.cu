@@ -38,7 +38,7 @@ struct DeviceInfo {
 std::mutex g_mu;
 std::atomic<int> g_reserved_sms{0};
 std::map<int, DeviceInfo> g_dev;
-std::map<std::pair<int, int>, float2*> g_tw;     // (device, +-nperseg) -> tables (negative: direct-DFT table)
+std::map<std::pair<int, int>, float2*> g_tw;     // (device, +-nperseg) -> tables (negative: direct-DFT table; + 2^20: mixed-radix table)
 
 int device_info(DeviceInfo& out, int& dev) {
     cudaError_t e = cudaGetDevice(&dev);
@@ -59,13 +59,14 @@ int device_info(DeviceInfo& out, int& dev) {
 
 // Twiddle table for nperseg on the current device; built on the host in double,
 // uploaded once (synchronously, first use only) and cached for the process.
-int twiddles(int dev, int nperseg, bool dft, const float2** out) {
+int twiddles(int dev, int nperseg, bool dft, const float2** out, bool mixed = false) {
     std::lock_guard<std::mutex> g(g_mu);
-    auto key = std::make_pair(dev, dft ? -nperseg : nperseg);
+    auto key = std::make_pair(dev, mixed ? nperseg + (1 << 20) : (dft ? -nperseg : nperseg));
     auto it = g_tw.find(key);
     if (it == g_tw.end()) {
         std::vector<float> host;
-        if (dft) b2s::make_dft_table(nperseg, host);
+        if (mixed) b2s::make_mixed_table(nperseg, host);
+        else if (dft) b2s::make_dft_table(nperseg, host);
         else b2s::make_tables(nperseg, host);
         float2* d = nullptr;
         cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float));
@@ -145,7 +146,7 @@ bool stream_capturing(cudaStream_t stream) {
 // diagnostic switches, read once per process
 struct EnvSwitches {
     bool allow_duo = true, duo1024 = true, allow_duo4 = true, allow_big = true, dynamic_units = true;
-    bool allow_pair = true, allow_pairq = false, fused_sum = true, sum_acc_smem = false;
+    bool allow_pair = true, allow_pairq = false, fused_sum = true, sum_acc_smem = false, allow_mixed = true;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
     int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
     int peer_timeout_ms = 0;     // B2S_PEER_TIMEOUT_MS: how long the peer all-reduce waits for a late rank (0: 120 s)
@@ -162,6 +163,7 @@ struct EnvSwitches {
         // (profiles/r2_pairq_vs_round1.md): opt-in
         allow_pairq = on("B2S_PAIRQ");
         fused_sum = !on("B2S_NO_FUSED_SUM");
+        allow_mixed = !on("B2S_NO_MIXED");
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
         if (const char* v = getenv("B2S_PAIR_NT")) pair_nt = atoi(v);
@@ -382,6 +384,39 @@ int launch_dft(const b2s::StftArgs& a, cudaStream_t stream) {
     return B2S_OK;
 }
 
+// mixed-radix family: one CTA per frame, grid-stride
+template <typename Tin>
+int launch_mixed(const b2s::StftArgs& a, cudaStream_t stream) {
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const void* kern = (const void*)b2s::mixed_psd_kernel<Tin>;
+    const size_t smem = b2s::mixed_smem_bytes(a.nperseg);
+    if ((int)smem > di.smem_optin) return fail(B2S_ERR_UNSUPPORTED, "b2s: nperseg too large for the mixed-radix kernel");
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        KernelState& ks = g_kern[kern];
+        if (ks.dev != dev) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            ks.dev = dev;
+            ks.occ = 1;
+        }
+    }
+    b2s::MixedParams mp{};
+    if (!b2s::fill_mixed_params(a, mp)) return fail(B2S_ERR_UNSUPPORTED, "b2s: nperseg has a prime factor above 13");
+    if (mp.d.total_frames == 0) return B2S_OK;
+    rc = twiddles(dev, a.nperseg, false, &mp.d.tw, true);
+    if (rc != B2S_OK) return rc;
+    const long long cap = (long long)di.sm_count * 8;
+    const long long grid = mp.d.total_frames < cap ? mp.d.total_frames : cap;
+    void* args[] = {&mp};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(b2s::kMixedThreads), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mixed-radix kernel launch");
+    return B2S_OK;
+}
+
 template <typename Tin>
 int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
                const float* window, int detrend, double scale, int out_mode, float db_floor, int kmin,
@@ -395,7 +430,12 @@ int stft_entry(const Tin* x, long long batch, long long n, long long x_batch_str
         int rc = b2s::validate_args(a, err);
         if (rc < 0) return fail(rc, err);
     }
-    if (b2s::nperseg_support(nperseg) == 2) {
+    const int support = b2s::nperseg_support(nperseg);
+    if (support == 3 && env().allow_mixed) {
+        b2s_note_kernel("mixed_psd_kernel (mixed-radix Stockham, one frame per CTA)", a);
+        return launch_mixed<Tin>(a, (cudaStream_t)stream);
+    }
+    if (support == 2 || support == 3) {
         b2s_note_kernel("dft_psd_kernel (direct DFT)", a);
         return launch_dft<Tin>(a, (cudaStream_t)stream);
     }
@@ -554,6 +594,7 @@ int b2s_set_option(const char* name, int value) {
     else if (n == "no_pair") e.allow_pair = !on;
     else if (n == "no_pairq") e.allow_pairq = !on;
     else if (n == "no_fused_sum") e.fused_sum = !on;
+    else if (n == "no_mixed") e.allow_mixed = !on;
     else if (n == "sum_acc_smem") e.sum_acc_smem = on;
     else if (n == "pair_units") e.pair_units = value;
     else if (n == "pair_nt") e.pair_nt = value;

@@ -10,6 +10,7 @@
 #include "../../include/b2s.h"
 #include "b2s_kernels.cuh"
 #include "b2s_dft_kernel.cuh"
+#include "b2s_mixed_kernel.cuh"
 
 namespace b2s {
 
@@ -89,12 +90,13 @@ inline long long frames_available(long long n, int nperseg, int hop) {
 // work units so that every group gets several runs of consecutive frames.
 constexpr int kMaxNperseg = 16384;
 
-// 1: radix-16 FFT kernels (powers of two 32..16384); 2: direct-DFT kernel (everything
-// else up to 16384); 0: unsupported.
+// 1: radix-16 FFT kernels (powers of two 32..16384); 3: mixed-radix kernel (other lengths >= 32 whose
+// prime factors are all <= 13); 2: direct-DFT kernel (everything else up to 16384); 0: unsupported.
 inline int nperseg_support(int nperseg) {
     if (nperseg < 1 || nperseg > kMaxNperseg) return 0;
     const int l = ilog2_exact(nperseg);
-    return (l >= 5 && l <= 14) ? 1 : 2;
+    if (l >= 5 && l <= 14) return 1;
+    return mixed_supported(nperseg) ? 3 : 2;
 }
 
 // Argument checks common to every kernel family (mirrors the shapes SciPy accepts).
@@ -270,6 +272,24 @@ namespace b2s {
 inline void make_dft_table(int nperseg, std::vector<float>& out) {
     out.assign(2 * (size_t)nperseg, 0.f);
     for (int j = 0; j < nperseg; ++j) put_w(out, j, j, nperseg);
+}
+
+// [Mc] W_Mc^j, then (even nperseg) [Mc + 1] W_N^k, for the mixed-radix kernel
+inline void make_mixed_table(int nperseg, std::vector<float>& out) {
+    const bool even = (nperseg % 2) == 0;
+    const int mc = even ? nperseg / 2 : nperseg;
+    out.assign(2 * (size_t)(mc + (even ? mc + 1 : 0)), 0.f);
+    for (int j = 0; j < mc; ++j) put_w(out, j, j, mc);
+    if (even)
+        for (int k = 0; k <= mc; ++k) put_w(out, mc + k, k, nperseg);
+}
+
+inline void fill_dft_params(const StftArgs& a, DftParams& p);
+inline bool fill_mixed_params(const StftArgs& a, MixedParams& mp) {
+    fill_dft_params(a, mp.d);
+    mp.mc = (a.nperseg % 2 == 0) ? a.nperseg / 2 : a.nperseg;
+    mp.npass = mixed_radices(mp.mc, mp.radix);
+    return mp.npass > 0;
 }
 
 inline void fill_dft_params(const StftArgs& a, DftParams& p) {

@@ -19,7 +19,7 @@ using namespace b2s;
 // which kernel family the last emu_stft_psd call ran (tests assert that a shape reaches the kernel it is meant for)
 static int g_last_family = 0;
 extern "C" int emu_last_family() { return g_last_family; }
-enum { FAM_PAIRQ = 10, FAM_PAIR = 9, FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
+enum { FAM_MIXED = 11, FAM_PAIRQ = 10, FAM_PAIR = 9, FAM_DUO256 = 1, FAM_DUO4 = 2, FAM_DUO_CTA = 3, FAM_DUO = 4, FAM_WARP = 5, FAM_BIG = 6, FAM_CTA = 7, FAM_DFT = 8 };
 
 struct EmuLauncher {
     StftParams p;
@@ -135,7 +135,20 @@ extern "C" int emu_stft_psd(const void* x, int x_is_f64, long long batch, long l
                db_floor, kmin, kmax, frame0, nframes, out, out_batch_stride, band_mode};
     std::string err;
     if (validate_args(a, err) < 0) return validate_args(a, err);
-    if (nperseg_support(nperseg) == 2) {
+    if (nperseg_support(nperseg) == 3 && !(getenv("B2S_NO_MIXED") && atoi(getenv("B2S_NO_MIXED")))) {
+        g_last_family = FAM_MIXED;
+        MixedParams mp{};
+        if (!fill_mixed_params(a, mp)) return -2;
+        std::vector<float> tw;
+        make_mixed_table(nperseg, tw);
+        mp.d.tw = reinterpret_cast<const float2*>(tw.data());
+        if (mp.d.total_frames == 0) return 0;
+        const unsigned g = (unsigned)(mp.d.total_frames < grid ? mp.d.total_frames : grid);
+        if (x_is_f64) emu::launch(g, kMixedThreads, mixed_smem_bytes(nperseg), [&] { mixed_psd_kernel<double>(mp); });
+        else emu::launch(g, kMixedThreads, mixed_smem_bytes(nperseg), [&] { mixed_psd_kernel<float>(mp); });
+        return 0;
+    }
+    if (nperseg_support(nperseg) >= 2) {
         g_last_family = FAM_DFT;
         DftParams dp{};
         fill_dft_params(a, dp);

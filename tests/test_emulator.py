@@ -324,6 +324,51 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
 
 
+@pytest.mark.parametrize("nperseg,hop", [(1000, 875), (96, 24), (160, 40), (2000, 500), (8000, 2000), (45, 10), (1001, 300),
+                                         (4800, 1200), (1100, 275), (8190, 4000), (16380, 16380)])
+@pytest.mark.parametrize("detrend", ["constant", False])
+def test_mixed_radix_kernel(emu, nperseg, hop, detrend, monkeypatch):
+    """Lengths that are not powers of two but factor into 2, 3, 5, 7, 11, 13 (the GUI accepts any integer
+    32..8192, GUI.py:87-89) run the mixed-radix Stockham kernel (b2s_mixed_kernel.cuh): even lengths through
+    the real-FFT trick, odd ones as a complex transform; crop / frame range / dB / band power / float64
+    samples; the direct-DFT kernel (B2S_NO_MIXED=1) as a second opinion."""
+    nfr = 4
+    n = nperseg + hop * (nfr - 1) + 3
+    x = signal(2, n, nperseg + hop, dc=-3.0 if detrend else 0.0)
+    kw = dict(window=("tukey", .25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = plan_for(n, 48000.0, **kw)
+    assert plan.nframes == nfr
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=48000.0, **kw)
+    So = np.moveaxis(So, -1, -2)
+    a = emu.stft_psd(x, plan, grid=3)
+    assert emu.last_family() == "mixed"
+    assert_parity(a, So, what=f"mixed {nperseg}/{hop}")
+    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan), a)
+    K = nperseg // 2 + 1
+    part = emu.stft_psd(x, plan, kmin=2, kmax=K - 3, frame0=1, nframes=nfr - 2)
+    assert np.array_equal(part, a[:, 1:nfr - 1, 2:K - 2])
+    band = emu.band_power(x, plan, 2, K - 3)
+    np.testing.assert_allclose(band, a[:, :, 2:K - 2].astype(np.float64).sum(axis=-1), rtol=3e-6)
+    floor = float(1e-6 * So.max())
+    db = emu.stft_psd(x, plan, out_mode=1, db_floor=floor)
+    big = So >= floor
+    assert np.max(np.abs(db - 10 * np.log10(np.maximum(So, floor)))[big]) <= 1e-3
+    monkeypatch.setenv("B2S_NO_MIXED", "1")
+    if nperseg <= 2000:                      # (the O(N^2) kernel is slow in the emulator)
+        d = emu.stft_psd(x, plan, grid=3)
+        assert emu.last_family() == "dft"
+        assert_parity(d, So, what=f"dft {nperseg}/{hop}")
+
+
+def test_mixed_radix_support_table():
+    """b2s_nperseg_support: 1 radix-16 kernels, 3 mixed radix, 2 direct DFT, 0 unsupported."""
+    from spectrogram_generator_b200 import _lib
+    lib = _lib.load()
+    for n, want in [(1000, 3), (2000, 3), (8000, 3), (96, 3), (4800, 3), (8190, 3), (1001, 3), (33, 3), (8191, 2), (34, 2),
+                    (31, 2), (62, 2), (1024, 1), (17 * 64, 2), (13 * 64, 3), (16383, 2), (16380, 3)]:
+        assert lib.b2s_nperseg_support(n) == want, n
+
+
 def test_sum_fused_plan_properties():
     """plan_stft_sum over random shapes: the blocks cover every sweep exactly once (ragged last
     block only), never exceed the cap, and the unit count matches blocks x even duo slots."""

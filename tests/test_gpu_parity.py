@@ -295,10 +295,12 @@ def test_runs_on_the_callers_stream_and_device_api():
     assert torch.equal(eng.stft_psd(wide[:, :30000], plan), a)
 
 
-@pytest.mark.parametrize("nperseg", [1000, 96, 160, 2000, 8000, 5, 31, 8191])
+@pytest.mark.parametrize("nperseg", [1000, 96, 160, 2000, 8000, 5, 31, 8191, 4800, 1001, 8190, 352, 544])
 def test_any_nperseg_direct_dft(nperseg):
     """GUI.py:87-89 lets the user type any nperseg in 32..8192; SciPy clamps nperseg to
-    len(x).  Non-power-of-two lengths run on the direct-DFT kernel -- same bar."""
+    len(x).  Non-power-of-two lengths run on the mixed-radix kernel when their prime factors are
+    all <= 13 and on the direct-DFT kernel otherwise (8191, 31, 5, 544 = 32 x 17) -- same bar; the
+    direct-DFT kernel is also held against every mixed-radix shape."""
     rng = np.random.default_rng(nperseg)
     n = max(20000, 5 * nperseg)
     t = np.arange(n) / 20000.0
@@ -306,7 +308,18 @@ def test_any_nperseg_direct_dft(nperseg):
     f, tt, S = sg.spectrogram(x, fs=20000.0, nperseg=nperseg, scaling="density", mode="psd")
     fr, tr, Sr = reference_path.reference_call(x.astype(np.float64), 20000.0, nperseg)
     assert np.array_equal(f, fr) and np.array_equal(tt, tr)
-    assert_parity(S, Sr, what=f"dft nperseg={nperseg}", tail=big_tail(S))
+    assert_parity(S, Sr, what=f"nperseg={nperseg}", tail=big_tail(S))
+    from spectrogram_generator_b200 import _lib
+    want = {3: "mixed_psd_kernel", 2: "dft_psd_kernel"}[_lib.load().b2s_nperseg_support(nperseg)]
+    assert _lib.last_kernel().startswith(want)
+    if want == "mixed_psd_kernel":
+        _lib.set_option("no_mixed", 1)
+        try:
+            _, _, Sd = sg.spectrogram(x, fs=20000.0, nperseg=nperseg, scaling="density", mode="psd")
+            assert _lib.last_kernel().startswith("dft_psd_kernel")
+        finally:
+            _lib.set_option("no_mixed", 0)
+        assert_parity(Sd, Sr, what=f"dft nperseg={nperseg}", tail=big_tail(Sd))
 
 
 def test_nperseg_clamped_to_odd_length():

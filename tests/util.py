@@ -188,7 +188,7 @@ class Emulator:
         assert rc == 0, rc
         return out
 
-    FAMILIES = {10: "pairq", 9: "pair", 1: "duo256", 2: "duo4", 3: "duo_cta", 4: "duo", 5: "warp", 6: "big", 7: "cta", 8: "dft"}
+    FAMILIES = {11: "mixed", 10: "pairq", 9: "pair", 1: "duo256", 2: "duo4", 3: "duo_cta", 4: "duo", 5: "warp", 6: "big", 7: "cta", 8: "dft"}
 
     def last_family(self):
         """Kernel family the last stft_psd / band_power call ran."""

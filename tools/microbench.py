@@ -77,6 +77,10 @@ def main():
     if args.set == "n1024ref":      # nperseg 1024 at the reference's default overlap and without overlap
         shapes += [(1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 1024, 896),
                    (1000, 40960, 1024, 1024)]
+    if args.set == "nonpow2":       # GUI-typed lengths (reference call form); B2S_NO_MIXED=1: the O(N^2) direct-DFT kernel
+        for nperseg in (1000, 2000, 4800, 8000, 96, 352):
+            shapes.append((1000, 40_000 if nperseg <= 2000 else 100_000, nperseg, nperseg - nperseg // 8, ("tukey", .25)))
+        shapes += [(1000, 40_000, 1000, 250), (1000, 40_000, 2000, 500)]
     if args.set == "n2048":
         shapes += [(1024, 100_000, 2048, 512)]
     if args.set == "n8192":
