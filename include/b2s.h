@@ -94,7 +94,7 @@ int b2s_peer_allreduce_status(void* stream);
 const char* b2s_last_error(void);
 
 /* 1 if `nperseg` runs on the fused radix-16 Stockham kernels (powers of two in
- * [32, 16384]), 3 if it runs on the mixed-radix kernel (other lengths >= 32 whose prime
+ * [32, 16384]), 3 if it runs on the mixed-radix kernel (other lengths >= 256 whose prime
  * factors are all <= 13, e.g. 1000, 2000, 4800, 8000), 2 if it runs on the direct-DFT kernel
  * (every other length in 1..16384: the GUI spin box allows any integer 32..8192,
  * GUI.py:87-89, and SciPy clamps nperseg to len(x), _spectral_py.py:2443-2447), 0 if

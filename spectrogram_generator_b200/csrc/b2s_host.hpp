@@ -90,7 +90,7 @@ inline long long frames_available(long long n, int nperseg, int hop) {
 // work units so that every group gets several runs of consecutive frames.
 constexpr int kMaxNperseg = 16384;
 
-// 1: radix-16 FFT kernels (powers of two 32..16384); 3: mixed-radix kernel (other lengths >= 32 whose
+// 1: radix-16 FFT kernels (powers of two 32..16384); 3: mixed-radix kernel (other lengths >= 256 whose
 // prime factors are all <= 13); 2: direct-DFT kernel (everything else up to 16384); 0: unsupported.
 inline int nperseg_support(int nperseg) {
     if (nperseg < 1 || nperseg > kMaxNperseg) return 0;

@@ -42,10 +42,11 @@ inline int mixed_radices(int mc, int* radix) {
     return (m == 1 && n > 0) ? n : 0;
 }
 
-// 1 if nperseg runs on this kernel (not a power of two >= 32 -- those have the radix-16 kernels --, at least 32,
-// and smooth)
+// true if nperseg runs on this kernel: not a power of two (those have the radix-16 kernels), smooth, and at
+// least 256 -- below that a 256-thread CTA per frame is mostly idle and the direct-DFT kernel is as fast or
+// faster (measured on B200, profiles/r2_nonpow2.md: nperseg 96 3.5 vs 5.2 ms, 352 5.7 vs 2.3 ms)
 inline bool mixed_supported(int nperseg) {
-    if (nperseg < 32 || nperseg > 16384) return false;
+    if (nperseg < 256 || nperseg > 16384) return false;
     if ((nperseg & (nperseg - 1)) == 0) return false;
     int r[kMixedMaxPasses];
     return mixed_radices((nperseg % 2 == 0) ? nperseg / 2 : nperseg, r) > 0;

@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
 def test_host_only_entries():
     lib = _lib.load()
     assert lib.b2s_version() == 1
-    for n, want in [(32, 1), (512, 1), (16384, 1), (16, 2), (1000, 3), (8191, 2), (96, 3), (34, 2), (1, 2), (0, 0), (32768, 0)]:
+    for n, want in [(32, 1), (512, 1), (16384, 1), (16, 2), (1000, 3), (8191, 2), (96, 2), (352, 3), (34, 2), (1, 2), (0, 0), (32768, 0)]:
         assert lib.b2s_nperseg_support(n) == want
     assert lib.b2s_frame_count(40000, 512, 128) == 309
     assert lib.b2s_frame_count(441000, 1024, 256) == 1719

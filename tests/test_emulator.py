@@ -324,7 +324,7 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
 
 
-@pytest.mark.parametrize("nperseg,hop", [(1000, 875), (96, 24), (160, 40), (2000, 500), (8000, 2000), (45, 10), (1001, 300),
+@pytest.mark.parametrize("nperseg,hop", [(1000, 875), (288, 72), (260, 65), (2000, 500), (8000, 2000), (315, 100), (1001, 300),
                                          (4800, 1200), (1100, 275), (8190, 4000), (16380, 16380)])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_mixed_radix_kernel(emu, nperseg, hop, detrend, monkeypatch):
@@ -364,8 +364,8 @@ def test_mixed_radix_support_table():
     """b2s_nperseg_support: 1 radix-16 kernels, 3 mixed radix, 2 direct DFT, 0 unsupported."""
     from spectrogram_generator_b200 import _lib
     lib = _lib.load()
-    for n, want in [(1000, 3), (2000, 3), (8000, 3), (96, 3), (4800, 3), (8190, 3), (1001, 3), (33, 3), (8191, 2), (34, 2),
-                    (31, 2), (62, 2), (1024, 1), (17 * 64, 2), (13 * 64, 3), (16383, 2), (16380, 3)]:
+    for n, want in [(1000, 3), (2000, 3), (8000, 3), (96, 2), (288, 3), (4800, 3), (8190, 3), (1001, 3), (33, 2), (8191, 2),
+                    (34, 2), (31, 2), (62, 2), (1024, 1), (17 * 64, 2), (13 * 64, 3), (16383, 2), (16380, 3), (255, 2), (260, 3)]:
         assert lib.b2s_nperseg_support(n) == want, n
 
 
