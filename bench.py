@@ -198,11 +198,22 @@ class ShapeBench:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t[0])
 
-    def time_ms(self, fn, iters=5, warm=2, flush=False):
+    def time_ms(self, fn, iters=7, warm_ms=25.0, flush=True):
+        """Median of `iters` launches, each bracketed by CUDA events, after at least 3 warm-up launches and
+        `warm_ms` of back-to-back launches.  Before every timed launch the L2 is flushed (a 192 MB memset in stream
+        order); besides defeating the cache this keeps the device busy while the host enqueues event - launch -
+        event, so the bracket does not contain the ~15 us the Python / ctypes call needs to reach cudaLaunchKernel
+        on an idle stream (measured: every shape reads a constant 15 us longer without it)."""
         torch = self.torch
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_warm = 0
+        while n_warm < 3 or (time.perf_counter() - t0) * 1e3 < warm_ms:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            n_warm += 3
+            if n_warm >= 300:
+                break
         if self.world > 1:
             self.dist.barrier()
         ts = []
@@ -215,13 +226,13 @@ class ShapeBench:
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        self.launches += iters + warm
+        self.launches += iters + n_warm
         return self.max_over_ranks(float(np.median(ts)))
 
     def plan(self, n, nperseg, hop, window="hann"):
         return self.sg.triage(n, 1.0, window, nperseg, nperseg - hop, None, "constant", True, "density", "psd")
 
-    def stft(self, name, batch, n, nperseg, hop, window="hann", iters=5, flush=False, global_batch=None,
+    def stft(self, name, batch, n, nperseg, hop, window="hann", iters=5, flush=True, global_batch=None,
              scaling="weak", note=None):
         """`batch` signals of `n` samples on THIS rank; global_batch: signals over all ranks."""
         torch = self.torch
@@ -252,7 +263,7 @@ class ShapeBench:
         sub = sg.Plan(**{**plan_g.__dict__, "n": hi - lo, "nframes": cnt})
         x = torch.randn((1, hi - lo), device=self.dev, dtype=torch.float32)
         out = torch.empty((1, cnt, plan_g.nbins), device=self.dev, dtype=torch.float32)
-        ms = self.time_ms(lambda: self.eng.stft_psd(x, sub, out=out), iters=5)
+        ms = self.time_ms(lambda: self.eng.stft_psd(x, sub, out=out))
         bytes_alg = 4 * n_total + 4 * plan_g.nframes * plan_g.nbins
         d = {"name": "C3 configs[2]: 1 h @ 48 kHz, frame ranges sharded over the ranks (halo nperseg - hop read-only)",
              "signals": 1, "samples_per_signal": n_total, "nperseg": nperseg, "hop": hop, "frames": plan_g.nframes,
@@ -279,7 +290,7 @@ class ShapeBench:
         x = torch.randn((max(rows, 1), n), device=self.dev, dtype=torch.float32)[:rows]
         out = torch.empty((rows, plan.nframes, plan.nbins), device=self.dev, dtype=torch.float32)
         fn = (lambda: self.eng.stft_psd(x, plan, out=out)) if rows else (lambda: None)
-        ms = self.time_ms(fn, iters=5)
+        ms = self.time_ms(fn)
         bytes_alg = 4 * channels * n + 4 * channels * plan.nframes * plan.nbins
         d = {"name": "C4 configs[3]: 16 channels x 60 s @ 96 kHz, PSD scaling, channels sharded over the ranks",
              "signals": channels, "samples_per_signal": n, "nperseg": nperseg, "hop": hop, "frames": plan.nframes,
@@ -648,9 +659,9 @@ def run_gpu(args):
         if shapes is not None:
             config["shapes"] = shapes
             config["shapes_note"] = ("each shape: one launch of the path on device-resident synthetic input, CUDA events, median "
-                                     "of 3-10 iterations after 2 warm-ups, max over ranks; frac = algorithmic bytes (4 B/sample in + "
-                                     "4 B/bin out) per GPU / ms / measured HBM peak; working sets exceed the L2 except C1 single "
-                                     "(L2 flushed between iterations); 'weak' = the stated batch per GPU, 'strong' = one problem "
+                                     "of 3-10 iterations after >= 25 ms of warm-up launches, max over ranks; frac = algorithmic bytes (4 B/sample in + "
+                                     "4 B/bin out) per GPU / ms / measured HBM peak; the L2 is flushed (192 MB memset in stream order) "
+                                     "before every timed launch; 'weak' = the stated batch per GPU, 'strong' = one problem "
                                      "cut over the ranks; gather_to_rank0_ms = the final gather to the exporting rank "
                                      "(NCCL send/recv), reported beside, not inside, the kernel time")
         if mg is not None:

@@ -51,7 +51,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="core")
     args = ap.parse_args()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = None if os.environ.get("B2S_MB_NOFLUSH") == "1" else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     shapes = []
     if args.set in ("core", "all"):
         shapes += [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 1024, 896),
