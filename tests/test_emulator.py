@@ -317,7 +317,8 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"{emu.last_family()} {nperseg}/{hop}")
     assert np.array_equal(a, b)
-    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
+    if not (pair and nperseg == 16384):      # (a float64 ring of 16384 samples does not fit: float64 takes the round-1 kernel)
+        assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
     part = emu.stft_psd(x, plan, kmin=3, kmax=500, frame0=1, nframes=nfr - 2, chunk=4)
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:501])
     band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
