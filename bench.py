@@ -253,6 +253,35 @@ class ShapeBench:
         del x, out
         return d
 
+    def stft_mean(self, name, batch, n, nperseg, hop, window="hann", iters=5):
+        """Per-sweep spectrograms AND their cross-sweep sum in one call (Engine.stft_psd_sum), timed in the fused
+        form and -- same call, b2s_set_option("no_fused_sum") -- as per-sweep kernel + two-pass sum."""
+        torch = self.torch
+        from spectrogram_generator_b200 import _lib
+        plan = self.plan(n, nperseg, hop, window)
+        x = torch.randn((batch, n), device=self.dev, dtype=torch.float32)
+        out = torch.empty((batch, plan.nframes, plan.nbins), device=self.dev, dtype=torch.float32)
+        tot = torch.empty((plan.nframes, plan.nbins), device=self.dev, dtype=torch.float32)
+        call = lambda: self.eng.stft_psd_sum(x, plan, post_scale=1.0 / batch, out=out, sum_out=tot)
+        ms = self.time_ms(call, iters=iters)
+        kernel = _lib.last_kernel()
+        _lib.set_option("no_fused_sum", 1)
+        try:
+            ms2 = self.time_ms(call, iters=iters)
+        finally:
+            _lib.set_option("no_fused_sum", 0)
+        gb = batch * self.world
+        bytes_alg = 4 * gb * n + 4 * gb * plan.nframes * plan.nbins
+        d = {"name": name, "signals": gb, "samples_per_signal": n, "nperseg": nperseg, "hop": hop,
+             "frames": plan.nframes, "ms": round(ms, 5), "gsamples_s": round(gb * n / ms / 1e6, 2),
+             "gbs_per_gpu": round(bytes_alg / self.world / ms / 1e6, 1),
+             "frac": round(bytes_alg / self.world / ms / 1e6 / self.peak, 4), "scaling": "weak", "kernel": kernel,
+             "ms_two_pass": round(ms2, 5),
+             "note": "rows + cross-sweep sum in one call; ms_two_pass: the same call as per-sweep kernel + two-pass sum "
+                     "(the rows read back once)"}
+        del x, out, tot
+        return d
+
     # C3: one long recording, contiguous frame ranges per rank (distributed.shard_frames / sample_span)
     def c3(self, n_total=172_800_000, nperseg=2048, hop=512):
         torch, sg = self.torch, self.sg
@@ -348,6 +377,8 @@ class ShapeBench:
         shapes.append(self.stft("C1 batched: 256 such signals per GPU in one launch", 256, 441_000, 1024, 256, iters=5))
         shapes.append(self.stft("north-star target: batched 1024-point STFT, 1000 x 40 000 per GPU, 75 % overlap",
                                 1000, 40_000, 1024, 256, iters=7))
+        shapes.append(self.stft_mean("north-star target shape with its mean: 1000 x 40 000 per GPU @ 1024/256, per-sweep "
+                                     "spectrograms + cross-sweep sum", 1000, 40_000, 1024, 256))
         shapes.append(self.stft("north-star target, the reference's own call form (PlotEngine.py:113: Tukey(0.25), "
                                 "noverlap = nperseg//8, GUI default nperseg 1024), 1000 x 200 000 per GPU",
                                 1000, 200_000, 1024, 896, window=("tukey", .25), iters=5))

@@ -517,6 +517,64 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
     return B2S_OK;
 }
 
+// nperseg 1024: the SUM mode of the staged-sample pair kernel (one pair of frames per warp over a block of
+// sweeps), then the fold over the sweep blocks.  Static schedule, planned like launch_duo_sum's.
+int launch_pair_sum(const b2s::StftArgs& a, float* sum_out, float post_scale, float* scratch, cudaStream_t stream) {
+    using PP = b2s::PairPlan<10>;
+    DeviceInfo di;
+    int dev = 0;
+    int rc = device_info(di, dev);
+    if (rc != B2S_OK) return rc;
+    const int tmem = env().sum_acc_smem ? 0 : 1;
+    const void* twin = b2s::pair_sum_kernel_for(a.x_is_f64, 0);
+    const void* kern = tmem ? b2s::pair_sum_kernel_for(a.x_is_f64, 1) : twin;
+    const int esz = a.x_is_f64 ? 8 : 4;
+    const size_t smem = PP::sum_smem_bytes(a.hop, esz);
+    const int smem_cap = di.smem_optin - 64;     // the tensor-memory kernel keeps its base-address slot in static shared memory
+    if ((int)smem > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this hop");
+    int occ = 0;
+    {
+        std::lock_guard<std::mutex> g(g_mu);
+        PairState& ks = g_pair[std::make_pair(kern, ((long long)dev << 40) | ((long long)PP::NT << 24) | (long long)smem)];
+        if (ks.occ == 0) {
+            // residency from the shared-memory twin (same register bound, same shared memory): the query
+            // answers 1 for a kernel that allocates tensor memory
+            cudaError_t e = cudaFuncSetAttribute(twin, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, twin, PP::NT, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            if (ks.occ < 1) ks.occ = 1;
+            if (ks.occ * PP::TMEM_COLS > 512) ks.occ = 512 / PP::TMEM_COLS;
+        }
+        occ = ks.occ;
+    }
+    const int fpc = PP::NT / 32;
+    const int reserve = (g_reserved_sms.load() < di.sm_count) ? g_reserved_sms.load() : di.sm_count - 1;
+    const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
+    b2s::StftParams p{};
+    std::string err;
+    const int blocks = b2s::plan_stft_sum(a, resident_ctas * fpc, kMaxSumBlocks, p, err, true);
+    if (blocks < 0) return fail(blocks, err);
+    if (p.n_units == 0) return B2S_OK;
+    p.acc = scratch;
+    p.ring = PP::ring_samples(a.hop);
+    rc = twiddles(dev, a.nperseg, false, &p.tw);
+    if (rc != B2S_OK) return rc;
+    const long long need = (p.n_units + fpc - 1) / fpc;
+    const long long grid = (need < resident_ctas) ? need : resident_ctas;
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)PP::NT), args, smem, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sum-fused pair kernel launch");
+    const long long elems = a.nframes * (a.nperseg / 2 + 1);
+    const int block = 256;
+    b2s::batch_sum_kernel<<<dim3((unsigned)((elems + block - 1) / block), 1), block, 0, stream>>>(
+        scratch, elems, blocks, blocks, elems, sum_out, post_scale);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
+    return B2S_OK;
+}
+
 template <typename Tin>
 int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch_stride, int nperseg, int hop,
                           const float* window, int detrend, double scale, long long frame0, long long nframes,
@@ -537,6 +595,12 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     if (slots) {
         b2s_note_kernel("stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
         return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
+    }
+    if (env().fused_sum && env().allow_duo && env().allow_pair && batch >= 2 &&
+        b2s::pair_kernel_ok(x, (int)(sizeof(Tin) == 8), batch, x_batch_stride, nperseg, hop, frame0) &&
+        reinterpret_cast<uintptr_t>(window) % 16 == 0) {
+        b2s_note_kernel("stft_psd_pair_sum_kernel (staged samples, running cross-sweep sums in tensor memory) + fold", a);
+        return launch_pair_sum(a, sum_out, post_scale, scratch, (cudaStream_t)stream);
     }
     // every other shape: the per-sweep kernel of its family, then the two-pass sum
     int rc = stft_entry<Tin>(x, batch, n, x_batch_stride, nperseg, hop, window, detrend, scale, B2S_OUT_LINEAR, 0.f, 0,

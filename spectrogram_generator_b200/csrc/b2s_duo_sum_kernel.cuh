@@ -17,37 +17,11 @@
 #pragma once
 
 #include "b2s_duo_kernel.cuh"
+#include "b2s_tmem.cuh"
 
 namespace b2s {
 
 
-#ifndef B2S_EMU
-// Tensor memory as per-thread scratch (no tensor-core math involved): with the 32x32b shape a
-// thread reads / writes N consecutive 32-bit columns of its own TMEM lane (warp w of the CTA owns
-// lanes 32 (w % 4) ... + 31).  The accesses go over the tensor-memory datapath, not the L1 /
-// shared-memory data pipe the rest of the kernel keeps busy.
-__device__ __forceinline__ void tm_ld4(unsigned addr, float& a, float& b, float& c, float& d) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
-}
-__device__ __forceinline__ void tm_ld2(unsigned addr, float& a, float& b) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr));
-}
-__device__ __forceinline__ void tm_ld_wait4(float& a, float& b, float& c, float& d) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b), "+f"(c), "+f"(d) : : "memory");
-}
-__device__ __forceinline__ void tm_ld_wait2(float& a, float& b) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b) : : "memory");
-}
-__device__ __forceinline__ void tm_st4(unsigned addr, float a, float b, float c, float d) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 : : "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ void tm_st2(unsigned addr, float a, float b) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" : : "r"(addr), "f"(a), "f"(b) : "memory");
-}
-__device__ __forceinline__ void tm_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" : : : "memory"); }
-#endif
 
 struct DuoSumPlan {
     static constexpr int ACC = 9 * DuoPlan::G;                          // float4 per duo

@@ -215,11 +215,13 @@ inline void plan_pair_units(const StftArgs& a, long long resident_warps, int uni
 // round-robin is balanced when the units fill the resident lane groups a whole number of times.
 // Fewest rounds x (rows + 1 for the start-up of a unit) wins, fewer blocks (less partial-sum
 // traffic) break ties.  Returns the number of blocks (<= max_blocks).
+// `pair_units`: the units of the staged-sample pair kernel's SUM mode (b2s_pair_kernel.cuh) -- one pair of
+// frames per WARP, so the units per block need not be even.
 inline int plan_stft_sum(const StftArgs& a, long long resident_groups, int max_blocks, StftParams& p,
-                         std::string& err) {
+                         std::string& err, bool pair_units = false) {
     const int log2n = plan_stft(a, 1, resident_groups, p, err, false);
     if (log2n < 0) return log2n;
-    const long long nduos = (a.nframes + 1) / 2, ups = (nduos + 1) / 2 * 2;
+    const long long nduos = (a.nframes + 1) / 2, ups = pair_units ? nduos : (nduos + 1) / 2 * 2;
     if (resident_groups < 1) resident_groups = 1;
     long long best_cost = -1, best_rows = a.batch > 0 ? a.batch : 1;
     for (long long nb = 1; nb <= max_blocks && nb <= a.batch; ++nb) {

@@ -16,6 +16,13 @@ static const void* pick(int slots) {
     }
 }
 
+// the SUM mode of the staged-sample pair kernel (nperseg 1024): sums in tensor memory, or the shared-memory twin
+const void* pair_sum_kernel_for(int x_is_f64, int acc_tmem) {
+    if (x_is_f64)
+        return acc_tmem ? (const void*)stft_psd_pair_sum_kernel<10, double, 2> : (const void*)stft_psd_pair_sum_kernel<10, double, 1>;
+    return acc_tmem ? (const void*)stft_psd_pair_sum_kernel<10, float, 2> : (const void*)stft_psd_pair_sum_kernel<10, float, 1>;
+}
+
 const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem) {
     if (x_is_f64) return acc_tmem ? pick<double, 1>(slots) : pick<double, 0>(slots);
     return acc_tmem ? pick<float, 1>(slots) : pick<float, 0>(slots);

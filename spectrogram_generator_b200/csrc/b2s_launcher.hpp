@@ -109,6 +109,9 @@ struct CudaLauncher {
 // acc_tmem: running sums in tensor memory (else shared memory)
 const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
 
+// the SUM mode of the staged-sample pair kernel, nperseg 1024 (b2s_inst_sum.cu)
+const void* pair_sum_kernel_for(int x_is_f64, int acc_tmem);
+
 // dispatch_tg<Tin, MODE> instantiated in b2s_inst_*.cu
 int dispatch_f32_plain(const StftArgs& a, CudaLauncher& L);
 int dispatch_f32_general(const StftArgs& a, CudaLauncher& L);

@@ -33,9 +33,22 @@
 // result of a frame depends on its samples only).  float64 samples are staged as float64 and the
 // coarse mean is subtracted in double before the cast, so a recording that sits on a large DC
 // level keeps its small signal (SciPy detrends float64 input in float64).
+//
+// SUM mode (stft_psd_pair_sum_kernel; per-sweep spectrograms AND their cross-sweep sum in one pass,
+// SURVEY.md 8 a-15, for nperseg 1024 at any staged hop): the same body walked in the other
+// direction.  A warp keeps ONE pair of frames (2 c, 2 c + 1) and walks over a block of consecutive
+// sweeps; the ring then holds the N + hop samples of that pair of one sweep, refilled by one bulk
+// copy per sweep, issued as soon as the sweep before has been consumed.  Every per-sweep row is
+// stored exactly as the per-sweep kernel stores it (same arithmetic, bit-identical), and the 33
+// power values a lane produces per frame are added, in sweep order, to running sums that never
+// leave the SM: tensor memory (SUM = 2, the product path: 34 columns of the lane's own TMEM lane)
+// or shared memory (SUM = 1: the CPU emulator's path and the twin the launch takes its residency
+// from).  A unit ends by writing its block's partial sums; batch_sum_kernel folds the blocks.
+// The order of the additions is fixed (sweep order in a block, block order in the fold).
 #pragma once
 
 #include "b2s_duo_cta_kernel.cuh"
+#include "b2s_tmem.cuh"
 
 namespace b2s {
 
@@ -58,12 +71,21 @@ struct PairPlan {
     static constexpr int OFF_W12 = OFF_TW1 + 8 * 16;     // [8][16] (W_1024^kap, W_1024^(2 kap)), kap = t + 16 pp
     static constexpr int OFF_W3 = OFF_W12 + 8 * 16;      // [8][16] float2 W_1024^(3 kap)  (half a float4 each)
     static constexpr int OFF_BUF = OFF_W3 + 4 * 16;      // nt/16 transpose buffers
-    B2S_HD static int off_bar(int nt) { return OFF_BUF + (nt / 16) * BUF; }   // nt/32 x 2 mbarriers (one float4 per warp)
+    // the wide CTA shape (nt > NT_MID) transposes real and imaginary parts one after the other through a
+    // half-size buffer: 12 KB of shared memory per warp instead of 16, i.e. 16 warps per SM where 13 fit
+    B2S_HD static int buf_f4(int nt) { return nt > NT_MID ? BUF / 2 : BUF; }
+    B2S_HD static int off_bar(int nt) { return OFF_BUF + (nt / 16) * buf_f4(nt); }   // nt/32 x 2 mbarriers (one float4 per warp)
     B2S_HD static int off_ring(int nt) { return off_bar(nt) + nt / 32; }     // nt/32 rings of ring_samples elements each
     // ring: the N + hop samples of a pair of frames, rounded up to 128 bytes
-    static int ring_samples(int hop) { return (N + hop + 31) / 32 * 32; }
-    static size_t smem_bytes(int hop, int esz, int nt = NT) {
+    B2S_HD static int ring_samples(int hop) { return (N + hop + 31) / 32 * 32; }
+    B2S_HD static size_t smem_bytes(int hop, int esz, int nt = NT) {
         return (size_t)off_ring(nt) * sizeof(float4) + (size_t)(nt / 32) * ring_samples(hop) * esz;
+    }
+    // SUM mode (128-thread CTAs): the running sums of the shared-memory twin, [9][NT] float4, behind the rings
+    static constexpr int ACC_SLOTS = 9;                  // 8 tasks x (kap, kap + 256, 512 - kap, 256 - kap) + (128, 384)
+    static constexpr int TMEM_COLS = 64;                 // 34 used
+    static size_t sum_smem_bytes(int hop, int esz) {
+        return smem_bytes(hop, esz, NT) + (size_t)ACC_SLOTS * NT * sizeof(float4);
     }
 };
 
@@ -164,7 +186,7 @@ struct EpiOne {
     }
 };
 
-template <int LOG2N, typename Tin, int MODE, int MINB>
+template <int LOG2N, typename Tin, int MODE, int MINB, int SUM = 0>
 B2S_DEVICE void stft_psd_pair_body(const StftParams& p);
 
 // 128 threads x 3 CTAs per SM
@@ -186,8 +208,15 @@ B2S_GLOBAL void B2S_MAXNREG(136) stft_psd_pair_mid_kernel(const StftParams p) {
     stft_psd_pair_body<LOG2N, Tin, MODE, 2>(p);
 }
 
-template <int LOG2N, typename Tin, int MODE, int MINB>
+// per-sweep rows + cross-sweep block sums (SUM = 1: sums in shared memory, 2: in tensor memory)
+template <int LOG2N, typename Tin, int SUM>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(PairPlan<LOG2N>::NT, 3) stft_psd_pair_sum_kernel(const StftParams p) {
+    stft_psd_pair_body<LOG2N, Tin, EPI_PLAIN, 3, SUM>(p);
+}
+
+template <int LOG2N, typename Tin, int MODE, int MINB, int SUM>
 B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
+    static_assert(SUM == 0 || (MODE == EPI_PLAIN && MINB == 3), "SUM mode: plain epilogue, 128-thread CTAs");
     using PL = Plan<LOG2N>;
     using PP = PairPlan<LOG2N>;
     constexpr int N = PP::N, M = PP::M, ROW = PP::ROW;
@@ -199,7 +228,8 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
     const int lane = tid & 31;
     const int h = lane >> 4;                             // frame of the pair this half-warp owns
     const int t = lane & 15;
-    float4* const buf = sm4 + PP::OFF_BUF + (tid >> 4) * PP::BUF;
+    constexpr bool HALF = (MINB == 1);                   // wide CTA: half-size transpose buffer
+    float4* const buf = sm4 + PP::OFF_BUF + (tid >> 4) * (HALF ? PP::BUF / 2 : PP::BUF);
     const int nt = (int)blockDim.x;
     const int nwarps = nt >> 5;
     unsigned long long* const bars = reinterpret_cast<unsigned long long*>(sm4 + PP::off_bar(nt) + warp);
@@ -231,7 +261,19 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
         }
         ring_fence_init();
     }
-    __syncthreads();
+    // SUM: the running sums of this lane, slot j = task pp (bins kap, kap + 256, 512 - kap, 256 - kap), slot 8 = (128, 384)
+    [[maybe_unused]] float4* const sacc = reinterpret_cast<float4*>(
+        reinterpret_cast<unsigned char*>(sm4) + PP::smem_bytes(p.hop, ESZ, PP::NT)) + tid;
+    [[maybe_unused]] unsigned tacc = 0;
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) {
+        __shared__ unsigned tmem_base_s;
+        tacc = tm_alloc_cta<PP::TMEM_COLS>(&tmem_base_s, tid);
+    } else
+#endif
+    {
+        __syncthreads();
+    }
 
     const int kout = p.kmax - p.kmin + 1;
     EpiOne<MODE> epi;
@@ -254,10 +296,25 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
         const Tin* x;        // first sample of the run
         float* out;          // row of the run's first frame (already offset by -kmin)
         int nf;              // frames in the run
+        int nit;             // iterations: pairs of frames of the run (SUM: sweeps of the block)
+        int blk, f0;         // SUM: sweep block, first frame of the pair
     };
     auto unit_of = [&](long long u) -> Unit {
         const long long b = u / p.units_per_signal;
         const int c = (int)(u - b * p.units_per_signal);
+        if constexpr (SUM != 0) {
+            // unit = (sweep block b, frame pair c), the pair index fastest: warps at work at the same time
+            // are on neighbouring frames of the same sweeps (their overlapping samples meet in L2)
+            const long long b_begin = b * p.acc_rows;
+            Unit r;
+            r.x = reinterpret_cast<const Tin*>(p.x) + b_begin * p.x_batch_stride + (p.frame0 + 2 * c) * (long long)p.hop;
+            r.out = p.out + b_begin * p.out_batch_stride + (long long)(2 * c) * kout;
+            r.nf = (2 * c + 1 < p.nframes) ? 2 : 1;
+            r.nit = (int)((b_begin + p.acc_rows < p.acc_batch) ? p.acc_rows : p.acc_batch - b_begin);
+            r.blk = (int)b;
+            r.f0 = 2 * c;
+            return r;
+        }
         const int f_begin = c * p.chunk_frames;
         const int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
         Unit r;
@@ -265,14 +322,19 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
         r.out = p.out + b * p.out_batch_stride +
                 ((MODE == EPI_BAND) ? (long long)f_begin : (long long)f_begin * kout - p.kmin);
         r.nf = f_end - f_begin;
+        r.nit = (r.nf + 1) >> 1;
+        r.blk = 0;
+        r.f0 = f_begin;
         return r;
     };
     // chunk j of a run of nf frames: j == 0 the first N + hop samples, then 2 hop per pair of frames,
     // cut at the run's last sample (span = (nf - 1) hop + N).  Returns the sample count (0: none).
     const int hop = p.hop;
+    // (SUM: chunk j is the whole pair of sweep j of the block -- span samples at ring position 0)
     auto chunk_lo = [&](int j) -> int { return j == 0 ? 0 : N + hop + 2 * hop * (j - 1); };
     auto chunk_len = [&](int nf, int j) -> int {
         const int span = (nf - 1) * hop + N;
+        if constexpr (SUM != 0) return span;
         const int lo = chunk_lo(j), hi = (j == 0) ? N + hop : lo + 2 * hop;
         const int e = hi < span ? hi : span;
         return e > lo ? e - lo : 0;
@@ -282,6 +344,15 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
     auto issue = [&](const Unit& un, int j) {
         const int len = chunk_len(un.nf, j);
         if (len == 0) return;                    // (warp-uniform)
+        if constexpr (SUM != 0) {
+            if (lane == 0) {
+                void* const bar = bars + (issued & 1u);
+                ring_expect(bar, (unsigned)(len * ESZ));
+                ring_copy(ring, un.x + (long long)j * p.x_batch_stride, (unsigned)(len * ESZ), bar);
+            }
+            ++issued;
+            return;
+        }
         if (lane == 0) {
             void* const bar = bars + (issued & 1u);
             const int lo = chunk_lo(j);
@@ -314,16 +385,31 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
     while (u_cur < p.n_units) {
         const bool have_next = u_next < p.n_units;
         if (have_next) unn = unit_of(u_next);
-        const int nit = (un.nf + 1) >> 1;
+        const int nit = un.nit;
         int pos = 0;                                     // ring position (samples) of frame 2 it
+        if constexpr (SUM != 0) {                        // the block sums start at zero; only this lane touches its slots
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tm_st4(tacc + 4 * j, 0.f, 0.f, 0.f, 0.f);
+                tm_st2(tacc + 32, 0.f, 0.f);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int j = 0; j < PP::ACC_SLOTS; ++j) sacc[j * PP::NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         for (int it = 0; it < nit; ++it) {
-            const int fr = 2 * it + h;                   // this half-warp's frame of the run
+            const int fr = (SUM != 0) ? h : 2 * it + h;  // this half-warp's frame of the run
             epi.act = fr < un.nf;
             epi.row = un.out + (long long)fr * kout;
+            if constexpr (SUM != 0) epi.row += (long long)it * p.out_batch_stride;
             wait_chunk(un, it);
 
             // ---- the frame's samples: slot i = x[4 (t + 16 i) .. + 3], 16 lanes read 256 contiguous bytes ----
             int w0 = pos + h * hop;                      // frame start in the ring (samples)
+            if constexpr (SUM != 0) w0 = epi.act ? h * hop : 0;    // (no frame B: transform frame A twice)
             if (w0 >= RS) w0 -= RS;
             w0 = w0 / 4 + t;                             // in float4s of samples, this lane's first slot
             const int RW4 = RS / 4;
@@ -429,16 +515,32 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
 
             // ---- sub-transforms: radix-16, 16 x 16 transpose inside the half-warp, radix-16 ----
             c2radix16(v);
+            if constexpr (HALF) {
+                float2* const b2 = reinterpret_cast<float2*>(buf);
+                float2 rr[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const cpx2 z = v[perm16(q)];
-                buf[ROW * t + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
-            }
-            __syncwarp();
+                for (int q = 0; q < 16; ++q) b2[ROW * t + q] = v[perm16(q)].re;
+                __syncwarp();
 #pragma unroll
-            for (int tt = 0; tt < 16; ++tt) {
-                const float4 q4 = buf[ROW * tt + t];
-                v[tt] = cpx2{cmk(q4.x, q4.y), cmk(q4.z, q4.w)};
+                for (int tt = 0; tt < 16; ++tt) rr[tt] = b2[ROW * tt + t];
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) b2[ROW * t + q] = v[perm16(q)].im;
+                __syncwarp();
+#pragma unroll
+                for (int tt = 0; tt < 16; ++tt) v[tt] = cpx2{rr[tt], b2[ROW * tt + t]};
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const cpx2 z = v[perm16(q)];
+                    buf[ROW * t + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int tt = 0; tt < 16; ++tt) {
+                    const float4 q4 = buf[ROW * tt + t];
+                    v[tt] = cpx2{cmk(q4.x, q4.y), cmk(q4.z, q4.w)};
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -453,7 +555,15 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
             // F_A = X_0 + i X_2, F_B = X_1 + i X_3 (X_r the spectrum of x[4 m + r]).  Task pp < 8 takes the
             // mirror F' = F[256 - kap] from lane 16 - t (its slot 15 - pp; lane 0 pairs kap = 16 pp with its own
             // slot 16 - pp, and kap = 0 with itself) and produces bins kap, kap + 256, 256 - kap, 512 - kap.
-            auto task = [&](cpx2 F, cpx2 G, float2 w1, float2 w2, float2 w3, int kap, bool dc, bool mid) {
+            auto task = [&](cpx2 F, cpx2 G, float2 w1, float2 w2, float2 w3, int kap, bool dc, bool mid, int slot) {
+                [[maybe_unused]] float4 a4;
+#ifndef B2S_EMU
+                if constexpr (SUM == 2) {
+                    if (slot == 0) tm_st_wait();                       // the previous sweep's updates have landed
+                    if (slot < 8) tm_ld4(tacc + 4 * slot, a4.x, a4.y, a4.z, a4.w);      // in flight during the butterfly below
+                    else tm_ld2(tacc + 32, a4.x, a4.y);
+                }
+#endif
                 const cpx2 U{pk_add(F.re, G.re), pk_sub(F.im, G.im)};       // (2 X_0, 2 X_1) = F + conj(F')
                 const cpx2 V{pk_add(F.im, G.im), pk_sub(G.re, F.re)};       // (2 X_2, 2 X_3) = -i (F - conj(F'))
                 // Y_r = W_1024^(r kap) 2 X_r
@@ -476,6 +586,27 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
                     epi.put(M - kap, ps.y);
                     if (!dc) epi.put(M / 2 - kap, pd.y);
                 }
+                if constexpr (SUM != 0) {
+                    // (kap, kap + 256 | 512 - kap, 256 - kap); slot 8 (lane 0's kap = 128): only the first two
+#ifndef B2S_EMU
+                    if constexpr (SUM == 2) {
+                        if (slot < 8) {
+                            tm_ld_wait4(a4.x, a4.y, a4.z, a4.w);
+                            const float2 a0 = pk_add(cmk(a4.x, a4.y), cmk(ps.x, pd.x)), a1 = pk_add(cmk(a4.z, a4.w), cmk(ps.y, pd.y));
+                            tm_st4(tacc + 4 * slot, a0.x, a0.y, a1.x, a1.y);
+                        } else {
+                            tm_ld_wait2(a4.x, a4.y);
+                            const float2 a0 = pk_add(cmk(a4.x, a4.y), cmk(ps.x, pd.x));
+                            tm_st2(tacc + 32, a0.x, a0.y);
+                        }
+                    } else
+#endif
+                    {
+                        a4 = sacc[slot * PP::NT];
+                        const float2 a0 = pk_add(cmk(a4.x, a4.y), cmk(ps.x, pd.x)), a1 = pk_add(cmk(a4.z, a4.w), cmk(ps.y, pd.y));
+                        sacc[slot * PP::NT] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                    }
+                }
             };
             const float2* const w3tab = reinterpret_cast<const float2*>(sm4 + PP::OFF_W3);
 #pragma unroll
@@ -489,11 +620,16 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
                 G.im = cmk(__shfl_sync(0xffffffffu, s2, partner), __shfl_sync(0xffffffffu, s3, partner));
                 const float4 w12 = sm4[PP::OFF_W12 + pp * 16 + t];
                 const float2 w3 = w3tab[pp * 16 + t];
-                task(F, G, cmk(w12.x, w12.y), cmk(w12.z, w12.w), w3, t + 16 * pp, pp == 0 && is0, false);
+                task(F, G, cmk(w12.x, w12.y), cmk(w12.z, w12.w), w3, t + 16 * pp, pp == 0 && is0, false, pp);
             }
-            if (is0) {                           // kap = 128 is its own mirror: bins 128 and 384
+            if (is0 || SUM == 2) {               // kap = 128 is its own mirror: bins 128 and 384 (lane 0's; the
+                                                 // tensor-memory accesses are warp-wide, so with SUM = 2 every lane goes
+                                                 // through the motions and only lane 0's stores and sums are used)
                 const cpx2 F = v[perm16(8)];
-                task(F, F, cmk(B2S_SQRT1_2, -B2S_SQRT1_2), cmk(0.f, -1.f), cmk(-B2S_SQRT1_2, -B2S_SQRT1_2), 128, false, true);
+                const bool keep = epi.act;
+                if constexpr (SUM == 2) epi.act = keep && is0;
+                task(F, F, cmk(B2S_SQRT1_2, -B2S_SQRT1_2), cmk(0.f, -1.f), cmk(-B2S_SQRT1_2, -B2S_SQRT1_2), 128, false, true, 8);
+                if constexpr (SUM == 2) epi.act = keep;
             }
             if constexpr (MODE == EPI_BAND) {
                 float bs = epi.band;
@@ -502,13 +638,54 @@ B2S_DEVICE void stft_psd_pair_body(const StftParams& p) {
                 for (int o = 8; o >= 1; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
                 if (is0 && epi.act) un.out[fr] = bs;
             }
-            pos += 2 * hop;
-            while (pos >= RS) pos -= RS;
+            if constexpr (SUM == 0) {
+                pos += 2 * hop;
+                while (pos >= RS) pos -= RS;
+            }
+        }
+        if constexpr (SUM != 0) {
+            // ---- the block's partial sums: p.acc[blk][frame][bin] ----
+            float4 a[PP::ACC_SLOTS];
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+                tm_st_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    tm_ld4(tacc + 4 * j, a[j].x, a[j].y, a[j].z, a[j].w);
+                    tm_ld_wait4(a[j].x, a[j].y, a[j].z, a[j].w);
+                }
+                a[8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tm_ld2(tacc + 32, a[8].x, a[8].y);
+                tm_ld_wait2(a[8].x, a[8].y);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int j = 0; j < PP::ACC_SLOTS; ++j) a[j] = sacc[j * PP::NT];
+            }
+            if (h < un.nf) {
+                float* const sA = p.acc + ((long long)un.blk * p.nframes + un.f0 + h) * (M + 1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kap = t + 16 * j;
+                    sA[kap] = a[j].x;
+                    sA[kap + M / 2] = a[j].y;
+                    sA[M - kap] = a[j].z;
+                    if (kap != 0) sA[M / 2 - kap] = a[j].w;
+                }
+                if (is0) {
+                    sA[128] = a[8].x;
+                    sA[128 + M / 2] = a[8].y;
+                }
+            }
         }
         u_cur = u_next;
         un = unn;
         if (have_next) u_next = dyn ? draw() : u_next + ustride;
     }
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) tm_free_cta<PP::TMEM_COLS>(tacc, tid);
+#endif
     if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
         __syncthreads();
         if (tid == 0) {

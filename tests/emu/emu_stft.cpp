@@ -57,7 +57,15 @@ struct EmuLauncher {
         if (pair_units >= 0) {
             plan_pair_units(a, (long long)grid * (PP::NT / 32), pair_units, dynamic_units, q);
         }
-        emu::launch(grid, PP::NT, PP::smem_bytes(a.hop, (int)sizeof(Tin)), [&] { stft_psd_pair_kernel<LOG2N, Tin, MODE>(q); });
+        int nt = PP::NT;
+        if (const char* v = getenv("B2S_PAIR_NT")) nt = atoi(v) / 32 * 32;
+        if (nt > PP::NT_WIDE) nt = PP::NT_WIDE;
+        if (nt < 32) nt = 32;
+        if (pair_units >= 0) plan_pair_units(a, (long long)grid * (nt / 32), pair_units, dynamic_units, q);
+        const size_t smem = PP::smem_bytes(a.hop, (int)sizeof(Tin), nt);
+        if (nt > PP::NT_MID) emu::launch(grid, nt, smem, [&] { stft_psd_pair_wide_kernel<LOG2N, Tin, MODE>(q); });
+        else if (nt > PP::NT) emu::launch(grid, nt, smem, [&] { stft_psd_pair_mid_kernel<LOG2N, Tin, MODE>(q); });
+        else emu::launch(grid, nt, smem, [&] { stft_psd_pair_kernel<LOG2N, Tin, MODE>(q); });
         return (work[0] == 0 && work[1] == 0) ? 0 : -100;
     }
     int pair_units = -1;         // >= 0: re-plan the runs with plan_pair_units (0: its default)
@@ -213,6 +221,29 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
                0.f, 0, nperseg / 2, frame0, nframes, out, out_batch_stride, 0};
     std::string err;
     if (validate_args(a, err) < 0) return validate_args(a, err);
+    const long long elems = nframes * (nperseg / 2 + 1);
+    if (nperseg == 1024) {
+        // the SUM mode of the staged-sample pair kernel (sums in shared memory: the twin of the product's
+        // tensor-memory kernel), `grid` resident CTAs of four warps
+        using PP = PairPlan<10>;
+        if (!pair_kernel_ok(x, x_is_f64, batch, x_batch_stride, nperseg, hop, frame0)) return -200;
+        StftParams p{};
+        const int blocks = plan_stft_sum(a, (long long)grid * (PP::NT / 32), max_blocks, p, err, true);
+        if (blocks < 0) return blocks;
+        std::vector<float> tw;
+        make_tables(nperseg, tw);
+        p.tw = reinterpret_cast<const float2*>(tw.data());
+        std::vector<float> part((size_t)blocks * elems, std::nanf(""));
+        p.acc = part.data();
+        p.ring = PP::ring_samples(hop);
+        const long long need = (p.n_units + PP::NT / 32 - 1) / (PP::NT / 32);
+        const unsigned g = (unsigned)(need < grid ? need : grid);
+        const size_t smem = PP::sum_smem_bytes(hop, x_is_f64 ? 8 : 4);
+        if (x_is_f64) emu::launch(g, PP::NT, smem, [&] { stft_psd_pair_sum_kernel<10, double, 1>(p); });
+        else emu::launch(g, PP::NT, smem, [&] { stft_psd_pair_sum_kernel<10, float, 1>(p); });
+        emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
+        return blocks;
+    }
     const int slots = duo_slots(a, ilog2_exact(nperseg));
     if (!slots || slots > 8) return -200;
     StftParams p{};
@@ -221,7 +252,6 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
     std::vector<float> tw;
     make_tables(nperseg, tw);
     p.tw = reinterpret_cast<const float2*>(tw.data());
-    const long long elems = nframes * (nperseg / 2 + 1);
     std::vector<float> part((size_t)blocks * elems, std::nanf(""));
     p.acc = part.data();
     const long long need = (p.n_units + DuoPlan::FPC - 1) / DuoPlan::FPC;

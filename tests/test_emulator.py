@@ -245,6 +245,32 @@ def test_sum_fused_duo_kernel(emu, hop, nframes, batch, grid, max_blocks):
     assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused duo 512/{hop}")
 
 
+@pytest.mark.parametrize("hop,detrend", [(256, "constant"), (128, False), (896, "constant"), (1024, False), (36, "constant")])
+@pytest.mark.parametrize("nframes,batch,grid,max_blocks", [(7, 5, 1, 64), (6, 9, 2, 4), (1, 3, 1, 2), (5, 2, 3, 1)])
+def test_sum_fused_pair_kernel(emu, hop, detrend, nframes, batch, grid, max_blocks):
+    """nperseg 1024: the SUM mode of the staged-sample pair kernel (a warp keeps one pair of frames and walks
+    over a block of sweeps, one bulk copy per sweep): the rows are bit-identical to the per-sweep kernel's, the
+    sum equals the float64 sum of the rows to fp32 rounding whatever the split into sweep blocks (odd frame
+    counts leave a half-empty pair, the last block is ragged); float64 samples likewise."""
+    n = 1024 + hop * (nframes - 1) + 4          # rows stay 16-byte aligned
+    x = signal(batch, n, hop + nframes + batch, dc=-2.0 if detrend else 0.0)
+    kw = dict(window=("tukey", 0.25), nperseg=1024, noverlap=1024 - hop, detrend=detrend)
+    plan = plan_for(n, 20000.0, **kw)
+    assert plan.nframes == nframes
+    rows = emu.stft_psd(x, plan, chunk=2)
+    assert emu.last_family() == "pair"
+    got, tot, blocks = emu.stft_psd_sum(x, plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert 1 <= blocks <= min(max_blocks, batch)
+    assert np.array_equal(got, rows)
+    want = 0.5 * rows.astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(tot, want, rtol=1e-6, atol=0)
+    got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert np.array_equal(got64, emu.stft_psd(x.astype(np.float64), plan, chunk=2))
+    np.testing.assert_allclose(tot64, want, rtol=2e-6, atol=0)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused pair 1024/{hop}")
+
+
 def test_sum_fused_plan_fills_the_grid():
     """plan_stft_sum on BASELINE config 2 with a B200's resident groups: one round, 22 blocks of 46."""
     import ctypes
@@ -323,6 +349,24 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:501])
     band = emu.band_power(x, plan, 0, nperseg // 2, chunk=3)
     np.testing.assert_allclose(band, a.astype(np.float64).sum(axis=-1), rtol=2e-6)
+
+
+@pytest.mark.parametrize("nt", [256, 512])
+@pytest.mark.parametrize("hop,detrend", [(256, "constant"), (896, False), (36, "constant")])
+def test_pair_kernel_cta_shapes(emu, nt, hop, detrend, monkeypatch):
+    """The staged-sample 1024 kernel's CTA shape is a launch parameter: the 384-thread shape and the wide one
+    (which transposes real and imaginary parts one after the other through a half-size buffer) give the same
+    bits as the 128-thread default."""
+    n = (1024 + hop * 10 + 11) // 4 * 4
+    x = signal(3, n, hop + 3, dc=5.0 if detrend else 0.0)
+    kw = dict(window="hann", nperseg=1024, noverlap=1024 - hop, detrend=detrend)
+    plan = plan_for(n, 20000.0, **kw)
+    a = emu.stft_psd(x, plan, grid=2)
+    assert emu.last_family() == "pair"
+    monkeypatch.setenv("B2S_PAIR_NT", str(nt))
+    b = emu.stft_psd(x, plan, grid=1)
+    assert np.array_equal(a, b)
+    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, grid=1), a)
 
 
 @pytest.mark.parametrize("nperseg,hop", [(1000, 875), (288, 72), (260, 65), (2000, 500), (8000, 2000), (315, 100), (1001, 300),

@@ -47,6 +47,39 @@ def time_shape(batch, n, nperseg, hop, iters=10, window="hann", detrend="constan
                 mb=round(bytes_alg / 1e6, 1))
 
 
+def time_mean(batch, n, nperseg, hop, iters=10, flush=None, fused=True):
+    """Engine.stft_psd_sum (rows + cross-sweep sum in one call); fused=False: b2s_set_option("no_fused_sum")."""
+    from spectrogram_generator_b200 import _lib
+    plan = sg.triage(n, 1.0, "hann", nperseg, nperseg - hop, None, "constant", True, "density", "psd")
+    eng = sg.engine()
+    x = torch.randn((batch, n), device="cuda", dtype=torch.float32)
+    out = torch.empty((batch, plan.nframes, plan.nbins), device="cuda", dtype=torch.float32)
+    tot = torch.empty((plan.nframes, plan.nbins), device="cuda", dtype=torch.float32)
+    _lib.set_option("no_fused_sum", 0 if fused else 1)
+    try:
+        for _ in range(3):
+            eng.stft_psd_sum(x, plan, out=out, sum_out=tot)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.stft_psd_sum(x, plan, out=out, sum_out=tot)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        kernel = _lib.last_kernel()
+    finally:
+        _lib.set_option("no_fused_sum", 0)
+    ms = float(np.median(ts))
+    bytes_alg = 4 * batch * n + 4 * batch * plan.nframes * plan.nbins
+    return dict(mean=True, fused=fused, batch=batch, n=n, nperseg=nperseg, hop=hop, frames=plan.nframes, ms=round(ms, 4),
+                ms_min=round(min(ts), 4), gsamples_s=round(batch * n / ms / 1e6, 2),
+                frac=round(bytes_alg / ms / 1e6 / peak(), 4), kernel=kernel.split(" (")[0])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="core")
@@ -94,6 +127,11 @@ def main():
         for nperseg in (256, 512, 1024, 2048, 4096, 8192, 16384):
             for ov in (0.5, 0.75, 0.875):
                 shapes.append((1024, 100_000, nperseg, int(nperseg * (1 - ov))))
+    if args.set == "mean":          # rows + cross-sweep sum in one call: fused kernels against per-sweep kernel + two-pass sum
+        for sh in [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 1024, 128), (1000, 40000, 1024, 512),
+                   (1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 256, 64)]:
+            for fused in (True, False):
+                print(json.dumps(time_mean(*sh, flush=flush, fused=fused)), flush=True)
     for s in shapes:
         kw = {"window": s[4]} if len(s) > 4 else {}
         print(json.dumps(time_shape(*s[:4], flush=flush, **kw)), flush=True)
