@@ -529,7 +529,9 @@ int launch_pair_sum(const b2s::StftArgs& a, float* sum_out, float post_scale, fl
     const void* twin = b2s::pair_sum_kernel_for(a.x_is_f64, 0);
     const void* kern = tmem ? b2s::pair_sum_kernel_for(a.x_is_f64, 1) : twin;
     const int esz = a.x_is_f64 ? 8 : 4;
-    const size_t smem = PP::sum_smem_bytes(a.hop, esz);
+    // (the tensor-memory kernel does not touch the twin's shared-memory sums: without them three CTAs share an
+    //  SM up to hop 256 where the twin's 18 KB more leave room for two)
+    const size_t smem = tmem ? PP::smem_bytes(a.hop, esz, PP::NT) : PP::sum_smem_bytes(a.hop, esz);
     const int smem_cap = di.smem_optin - 64;     // the tensor-memory kernel keeps its base-address slot in static shared memory
     if ((int)smem > smem_cap) return fail(B2S_ERR_UNSUPPORTED, "b2s: shared memory per block too small for this hop");
     int occ = 0;
@@ -554,7 +556,13 @@ int launch_pair_sum(const b2s::StftArgs& a, float* sum_out, float post_scale, fl
     const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
     b2s::StftParams p{};
     std::string err;
-    const int blocks = b2s::plan_stft_sum(a, resident_ctas * fpc, kMaxSumBlocks, p, err, true);
+    // The split into sweep blocks fixes the order of the additions.  It is planned from the residency a launch
+    // on float samples would have (three CTAs per SM where their rings fit), so that float64 samples -- bigger
+    // rings, sometimes one CTA fewer per SM -- give the same sums bit for bit.
+    int occ_plan = 3;
+    while (occ_plan > 1 && (long long)occ_plan * (PP::smem_bytes(a.hop, 4, PP::NT) + 1024) > (long long)di.smem_optin + 1024) --occ_plan;
+    const long long plan_groups = (long long)(di.sm_count - reserve) * occ_plan * fpc;
+    const int blocks = b2s::plan_stft_sum(a, plan_groups, kMaxSumBlocks, p, err, true);
     if (blocks < 0) return fail(blocks, err);
     if (p.n_units == 0) return B2S_OK;
     p.acc = scratch;

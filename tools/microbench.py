@@ -132,6 +132,8 @@ def main():
                    (1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 256, 64)]:
             for fused in (True, False):
                 print(json.dumps(time_mean(*sh, flush=flush, fused=fused)), flush=True)
+    if args.set == "mean1024":      # one shape, for ncu
+        print(json.dumps(time_mean(1000, 40000, 1024, 256, iters=3, flush=flush)), flush=True)
     for s in shapes:
         kw = {"window": s[4]} if len(s) > 4 else {}
         print(json.dumps(time_shape(*s[:4], flush=flush, **kw)), flush=True)
