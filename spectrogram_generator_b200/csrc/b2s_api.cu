@@ -463,18 +463,24 @@ constexpr int kMaxSumBlocks = 64;       // sweep blocks of the sum-fused kernel:
 
 // the sum-fused frame-duo kernel (per-sweep rows and their cross-sweep sum in one pass), then the
 // fold over its sweep blocks.  Static schedule: plan_stft_sum makes the units fill the grid evenly.
-int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post_scale, float* scratch,
-                   cudaStream_t stream) {
-    using DP = b2s::DuoPlan;
+struct SumKernelShape {
+    const void* kern;        // the launch's kernel (running sums in tensor memory, or the twin)
+    const void* twin;        // the shared-memory twin: residency is taken from it
+    int nt, fpc;             // CTA threads, lane groups (duos in flight) per CTA
+    size_t smem;             // dynamic shared memory (both)
+    int tmem_cols;           // tensor-memory columns a CTA allocates
+    int duos_per_warp;       // plan_stft_sum's unit multiple
+};
+
+int launch_sum_kernel(const b2s::StftArgs& a, const SumKernelShape& ks_in, float* sum_out, float post_scale, float* scratch,
+                      cudaStream_t stream) {
     DeviceInfo di;
     int dev = 0;
     int rc = device_info(di, dev);
     if (rc != B2S_OK) return rc;
-    const int tmem = env().sum_acc_smem ? 0 : 1;
-    const void* twin = b2s::duo_sum_kernel_for(a.x_is_f64, slots, 0);
-    const void* kern = tmem ? b2s::duo_sum_kernel_for(a.x_is_f64, slots, 1) : twin;
-    if (!kern || !twin) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
-    const size_t smem = b2s::DuoSumPlan::SMEM;
+    const void* const kern = ks_in.kern;
+    const void* const twin = ks_in.twin;
+    const size_t smem = ks_in.smem;
     int occ = 0;
     {
         std::lock_guard<std::mutex> g(g_mu);
@@ -485,10 +491,10 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
             cudaError_t e = cudaFuncSetAttribute(twin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, twin, DP::NT, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ks.occ, twin, ks_in.nt, smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
             if (ks.occ < 1) ks.occ = 1;
-            if (ks.occ * b2s::DuoSumPlan::TMEM_COLS > 512) ks.occ = 512 / b2s::DuoSumPlan::TMEM_COLS;
+            if (ks.occ * ks_in.tmem_cols > 512) ks.occ = 512 / ks_in.tmem_cols;
             ks.dev = dev;
         }
         occ = ks.occ;
@@ -497,16 +503,16 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
     const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
     b2s::StftParams p{};
     std::string err;
-    const int blocks = b2s::plan_stft_sum(a, resident_ctas * DP::FPC, kMaxSumBlocks, p, err);
+    const int blocks = b2s::plan_stft_sum(a, resident_ctas * ks_in.fpc, kMaxSumBlocks, p, err, ks_in.duos_per_warp);
     if (blocks < 0) return fail(blocks, err);
     if (p.n_units == 0) return B2S_OK;
     p.acc = scratch;
     rc = twiddles(dev, a.nperseg, false, &p.tw);
     if (rc != B2S_OK) return rc;
-    const long long need = (p.n_units + DP::FPC - 1) / DP::FPC;
+    const long long need = (p.n_units + ks_in.fpc - 1) / ks_in.fpc;
     const long long grid = (need < resident_ctas) ? need : resident_ctas;
     void* args[] = {&p};
-    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)DP::NT), args, smem, stream);
+    cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3((unsigned)ks_in.nt), args, smem, stream);
     if (e != cudaSuccess) return cuda_fail(e, "sum-fused stft kernel launch");
     const long long elems = a.nframes * (a.nperseg / 2 + 1);
     const int block = 256;
@@ -515,6 +521,28 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "batch_sum_kernel launch");
     return B2S_OK;
+}
+
+// the sum-fused frame-duo kernels (per-sweep rows and their cross-sweep sum in one pass), then the
+// fold over the sweep blocks.  Static schedule: plan_stft_sum makes the units fill the grid evenly.
+int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post_scale, float* scratch,
+                   cudaStream_t stream) {
+    const int tmem = env().sum_acc_smem ? 0 : 1;
+    SumKernelShape ks{};
+    if (a.nperseg == 256) {
+        using DP = b2s::Duo256Plan;
+        ks.twin = b2s::duo256_sum_kernel_for(a.x_is_f64, slots, 0);
+        ks.kern = tmem ? b2s::duo256_sum_kernel_for(a.x_is_f64, slots, 1) : ks.twin;
+        ks.nt = DP::NT, ks.fpc = DP::FPC, ks.smem = DP::SUM_SMEM, ks.tmem_cols = DP::TMEM_COLS, ks.duos_per_warp = 4;
+    } else {
+        using DP = b2s::DuoPlan;
+        ks.twin = b2s::duo_sum_kernel_for(a.x_is_f64, slots, 0);
+        ks.kern = tmem ? b2s::duo_sum_kernel_for(a.x_is_f64, slots, 1) : ks.twin;
+        ks.nt = DP::NT, ks.fpc = DP::FPC, ks.smem = b2s::DuoSumPlan::SMEM, ks.tmem_cols = b2s::DuoSumPlan::TMEM_COLS;
+        ks.duos_per_warp = 2;
+    }
+    if (!ks.kern || !ks.twin) return fail(B2S_ERR_UNSUPPORTED, "b2s: no sum-fused kernel for this hop");
+    return launch_sum_kernel(a, ks, sum_out, post_scale, scratch, stream);
 }
 
 // nperseg 1024: the SUM mode of the staged-sample pair kernel (one pair of frames per warp over a block of
@@ -562,7 +590,7 @@ int launch_pair_sum(const b2s::StftArgs& a, float* sum_out, float post_scale, fl
     int occ_plan = 3;
     while (occ_plan > 1 && (long long)occ_plan * (PP::smem_bytes(a.hop, 4, PP::NT) + 1024) > (long long)di.smem_optin + 1024) --occ_plan;
     const long long plan_groups = (long long)(di.sm_count - reserve) * occ_plan * fpc;
-    const int blocks = b2s::plan_stft_sum(a, plan_groups, kMaxSumBlocks, p, err, true);
+    const int blocks = b2s::plan_stft_sum(a, plan_groups, kMaxSumBlocks, p, err, 1);
     if (blocks < 0) return fail(blocks, err);
     if (p.n_units == 0) return B2S_OK;
     p.acc = scratch;
@@ -599,9 +627,11 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     if (nframes < 1 || batch < 1) return fail(B2S_ERR_BAD_ARG, "b2s_stft_psd_sum: nothing to sum");
     const long long elems = nframes * (nperseg / 2 + 1);
     int slots = (!env().fused_sum || !env().allow_duo || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
-    if (slots > 8) slots = 0;           // hop 448 / 512: per-sweep frame-duo kernel, no sum-fused variant
+    if (slots > 8) slots = 0;           // hop 7/8 nperseg and nperseg: per-sweep frame-duo kernel, no sum-fused variant
+    if (nperseg == 256 && env().fused_sum && env().allow_duo && batch >= 2) slots = b2s::duo256_sum_slots(a, 8);
     if (slots) {
-        b2s_note_kernel("stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
+        b2s_note_kernel(nperseg == 256 ? "stft_psd_duo256_sum_kernel (frame duo, 8 lanes, running cross-sweep sums in tensor memory) + fold"
+                                       : "stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
         return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
     }
     if (env().fused_sum && env().allow_duo && env().allow_pair && batch >= 2 &&

@@ -63,6 +63,15 @@ inline int duo_slots(const StftArgs& a, int log2n) {
     return (s == 2 || s == 4 || s == 8 || s == 14) ? (int)s : 16;
 }
 
+// sum-fused 256-point frame-duo kernel (SUM mode of b2s_duo256_kernel.cuh): S = hop / 16 for hop 32 / 64 / 128
+// (the same register layout and detrend tree as the per-sweep kernel of that hop: bit-identical rows); any other
+// even hop takes S = 16, which holds both frames whole -- the per-sweep kernels of those hops (S = 14, 16) use
+// the same per-frame arithmetic.
+inline int duo256_sum_slots(const StftArgs& a, int log2n) {
+    if (log2n != 8 || !frames_vec_aligned(a)) return 0;
+    return (a.hop == 32) ? 2 : (a.hop == 64) ? 4 : (a.hop == 128) ? 8 : 16;
+}
+
 template <typename Tin, int MODE, class Launcher>
 int dispatch_duo(const StftArgs& a, Launcher& L, int s) {
     switch (s) {

@@ -9,9 +9,16 @@
 //     is in its first column.  Lane 4 is its own partner and needs nothing special; lane 0 pairs
 //     inside its own columns (16 p with 16 (8 - p), 8 + 16 p with 8 + 16 (7 - p)) and selects
 //     its operands, twiddles and bins accordingly.
+//
+// SUM mode (stft_psd_duo256_sum_kernel: per-sweep spectrograms AND their cross-sweep sum in one pass,
+// SURVEY.md 8 a-15): as in b2s_duo_sum_kernel.cuh a lane group keeps ONE frame duo and walks over a
+// block of consecutive sweeps, loading all its 16 + S slots afresh one sweep ahead; rows bit-identical
+// to the per-sweep kernel's, the 2 x 129 power values added in sweep order into 34 running sums per
+// lane -- tensor memory (SUM = 2, the product path) or shared memory (SUM = 1: emulator / residency twin).
 #pragma once
 
 #include "b2s_duo_cta_kernel.cuh"
+#include "b2s_tmem.cuh"
 
 namespace b2s {
 
@@ -29,13 +36,32 @@ struct Duo256Plan {
     static constexpr int OFF_TWP = OFF_TW + 8 * 8;       // [4][8]  split twiddles of pairs 2j, 2j+1 (lane 0: its own bins)
     static constexpr int TAB = OFF_TWP + 4 * 8;
     static constexpr size_t SMEM = (size_t)(TAB + FPC * BUF) * sizeof(float4);
+    // SUM mode: the shared-memory twin's running sums, [9][NT] float4 behind the transpose buffers
+    static constexpr int ACC_SLOTS = 9;                  // 8 pairs x (k: A, B; 128 - k: A, B) + bin 64
+    static constexpr size_t SUM_SMEM = SMEM + (size_t)ACC_SLOTS * NT * sizeof(float4);
+    static constexpr int TMEM_COLS = 64;                 // 34 used
 };
 
 // low bin of pair pp for lane q: q + 16 pp, except lane 0 (16 pp for pp < 4, then 8 + 16 (pp - 4))
 B2S_HD int duo256_low_bin(int q, int pp) { return (q != 0) ? q + 16 * pp : ((pp < 4) ? 16 * pp : 8 + 16 * (pp - 4)); }
 
+template <typename Tin, int S, int MODE, int SUM>
+B2S_DEVICE void stft_psd_duo256_body(const StftParams& p);
+
 template <typename Tin, int S, int MODE>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo256_kernel(const StftParams p) {
+    stft_psd_duo256_body<Tin, S, MODE, 0>(p);
+}
+// per-sweep rows + cross-sweep block sums (SUM = 1: sums in shared memory, 2: in tensor memory); p.units_per_signal =
+// duos per block rounded up to a multiple of 4 (the four duos of a warp share a block), plan_stft_sum(..., 4)
+template <typename Tin, int S, int SUM>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo256_sum_kernel(const StftParams p) {
+    stft_psd_duo256_body<Tin, S, EPI_PLAIN, SUM>(p);
+}
+
+template <typename Tin, int S, int MODE, int SUM>
+B2S_DEVICE void stft_psd_duo256_body(const StftParams& p) {
+    static_assert(SUM == 0 || MODE == EPI_PLAIN, "SUM mode: plain epilogue");
     using DP = Duo256Plan;
     using PL = Plan<8>;
     constexpr int M = DP::M, G = DP::G, ROW = DP::ROW;
@@ -71,7 +97,17 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
             }
         }
     }
-    __syncthreads();
+    [[maybe_unused]] float4* const sacc = sm4 + DP::TAB + DP::FPC * DP::BUF + tid;     // [slot][NT]
+    [[maybe_unused]] unsigned tacc = 0;
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) {
+        __shared__ unsigned tmem_base_s;
+        tacc = tm_alloc_cta<DP::TMEM_COLS>(&tmem_base_s, tid);
+    } else
+#endif
+    {
+        __syncthreads();
+    }
 
     const int kout = p.kmax - p.kmin + 1;
     const int partner = (tid & 24) | ((8 - t) & 7);
@@ -94,12 +130,26 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
         long long u = ub + (grp & 3);
         const bool uvalid = u < p.n_units;
         if (!uvalid) u = p.n_units - 1;
-        const long long b = u / p.units_per_signal;
-        const int c = (int)(u - b * p.units_per_signal);
-        const int f_begin = c * p.chunk_frames;
-        const int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
-        const Tin* const xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop + 2 * t;
-        float* const ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
+        long long b = u / p.units_per_signal;
+        int c = (int)(u - b * p.units_per_signal);
+        int f_begin = c * p.chunk_frames;
+        int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
+        [[maybe_unused]] int blk = 0, nsweeps = 0;
+        [[maybe_unused]] bool svalid = true;
+        if constexpr (SUM != 0) {
+            // unit = (sweep block, duo c), the duo index fastest; the run is the one duo (frames 2 c, 2 c + 1)
+            // of the block's first sweep, and the loop below walks the sweeps instead of the frames
+            blk = (int)b;
+            const int nduos = (p.nframes + 1) >> 1;
+            svalid = c < nduos;
+            if (!svalid) c = nduos - 1;
+            f_begin = 2 * c;
+            f_end = (f_begin + 2 < p.nframes) ? f_begin + 2 : p.nframes;
+            b = (long long)blk * p.acc_rows;
+            nsweeps = (int)((b + p.acc_rows < p.acc_batch) ? p.acc_rows : p.acc_batch - b);
+        }
+        const Tin* xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop + 2 * t;
+        float* ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
 
         // raw samples of the duo: slot i <-> complex index t + 8 i relative to frame f
         float2 cur[NCUR];
@@ -111,7 +161,20 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
         }
         // the four duos of a warp run the same trip count (the longest run's)
         int ntrip = uvalid ? (f_end - f_begin + 1) >> 1 : 0;
-        {
+        if constexpr (SUM != 0) {
+            ntrip = nsweeps;                     // (warp-uniform: the four duos of a warp share the block)
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) tm_st4(tacc + 4 * j, 0.f, 0.f, 0.f, 0.f);
+                tm_st2(tacc + 32, 0.f, 0.f);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int j = 0; j < DP::ACC_SLOTS; ++j) sacc[j * DP::NT] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
             int o = __shfl_xor_sync(0xffffffffu, ntrip, 8);
             ntrip = ntrip > o ? ntrip : o;
             o = __shfl_xor_sync(0xffffffffu, ntrip, 16);
@@ -119,9 +182,9 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
         }
 
         int f = f_begin;
-        for (int it = 0; it < ntrip; ++it, f += 2) {
-            const bool actA = uvalid && (f < f_end);
-            const bool actB = uvalid && (f + 1 < f_end);
+        for (int it = 0; it < ntrip; ++it, f += (SUM != 0 ? 0 : 2)) {
+            const bool actA = uvalid && svalid && (f < f_end);
+            const bool actB = uvalid && svalid && (f + 1 < f_end);
 
             // ---- detrend + window, packing frame A (slots 0..15) and B (slots S..S+15) ----
             cpx2 v[16];
@@ -203,7 +266,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
             }
 
             // ---- next duo (frames f+2, f+3): keep the overlap, prefetch the 2 S new slots ----
-            {
+            if constexpr (SUM != 0) {            // the same duo of the next sweep: all 16 + S slots, one sweep ahead
+                if (it + 1 < ntrip) xb += p.x_batch_stride;
+                const Tin* const xn = xb + (long long)f * p.hop;
+                const Tin* const xnB = xn + bskew - ((f + 1 < f_end) ? 0 : p.hop);
+#pragma unroll
+                for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xn : xnB) + 16 * i);
+            } else {
 #pragma unroll
                 for (int i = 0; i < KEEP; ++i) cur[i] = cur[i + 2 * S];
                 const int fa = (f + 2 < f_end) ? f + 2 : f_end - 1;
@@ -263,6 +332,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
                 // general lane: Z[t + 16 pp] with the partner's second column at 7 - pp.
                 // lane 0 (its own partner): pp < 4: Z[16 pp] with Z[16 ((8 - pp) & 7)] (pp = 0: itself);
                 //                           pp >= 4: Z[8 + 16 (pp - 4)] with Z[8 + 16 (11 - pp)]
+                [[maybe_unused]] float4 a4;
+#ifndef B2S_EMU
+                if constexpr (SUM == 2) {
+                    if (pp == 0) tm_st_wait();                         // the previous sweep's updates have landed
+                    tm_ld4(tacc + 4 * pp, a4.x, a4.y, a4.z, a4.w);     // in flight during the butterfly below
+                }
+#endif
                 cpx2 zk = c1[pp];
                 const cpx2 sg = c2[7 - pp];
                 const cpx2 s0 = (pp < 4) ? c1[(8 - pp) & 7] : c2[11 - pp];
@@ -291,12 +367,42 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
                 const int k = duo256_low_bin(t, pp);
                 put(k, pk);
                 put(M - k, pm);
+                if constexpr (SUM != 0) {
+#ifndef B2S_EMU
+                    if constexpr (SUM == 2) {
+                        tm_ld_wait4(a4.x, a4.y, a4.z, a4.w);
+                        const float2 a0 = pk_add(cmk(a4.x, a4.y), pk), a1 = pk_add(cmk(a4.z, a4.w), pm);
+                        tm_st4(tacc + 4 * pp, a0.x, a0.y, a1.x, a1.y);
+                    } else
+#endif
+                    {
+                        a4 = sacc[pp * DP::NT];
+                        const float2 a0 = pk_add(cmk(a4.x, a4.y), pk), a1 = pk_add(cmk(a4.z, a4.w), pm);
+                        sacc[pp * DP::NT] = make_float4(a0.x, a0.y, a1.x, a1.y);
+                    }
+                }
             }
             {   // k = 64: X = conj(Z[64]), held by lane 0 (first column, pp = 4)
                 const cpx2 z = c1[4];
                 const float2 pw = pk_muls(pk_fma(z.re, z.re, pk_mul(z.im, z.im)), 4.0f);
                 if (is0) put(M / 2, pw);
+                if constexpr (SUM != 0) {
+#ifndef B2S_EMU
+                    if constexpr (SUM == 2) {        // (warp-wide accesses: every lane keeps such a sum, lane 0's is used)
+                        float2 am;
+                        tm_ld2(tacc + 32, am.x, am.y);
+                        tm_ld_wait2(am.x, am.y);
+                        am = pk_add(am, pw);
+                        tm_st2(tacc + 32, am.x, am.y);
+                    } else
+#endif
+                    {
+                        float2* const q = reinterpret_cast<float2*>(sacc + 8 * DP::NT);
+                        *q = pk_add(*q, pw);
+                    }
+                }
             }
+            if constexpr (SUM != 0) ob += p.out_batch_stride;
             if constexpr (MODE == EPI_BAND) {
 #pragma unroll
                 for (int o = G / 2; o >= 1; o >>= 1)
@@ -307,7 +413,49 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo256Plan::NT, Duo256Plan::MINB) stft_psd_duo
                 }
             }
         }
+        if constexpr (SUM != 0) {
+            // ---- the block's partial sums: p.acc[blk][frame][bin] ----
+            float4 a[DP::ACC_SLOTS];
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+                tm_st_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    tm_ld4(tacc + 4 * j, a[j].x, a[j].y, a[j].z, a[j].w);
+                    tm_ld_wait4(a[j].x, a[j].y, a[j].z, a[j].w);
+                }
+                a[8] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tm_ld2(tacc + 32, a[8].x, a[8].y);
+                tm_ld_wait2(a[8].x, a[8].y);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int j = 0; j < DP::ACC_SLOTS; ++j) a[j] = sacc[j * DP::NT];
+            }
+            if (uvalid && svalid) {
+                const bool hasB = f_begin + 1 < p.nframes;
+                float* const sA = p.acc + ((long long)blk * p.nframes + f_begin) * (M + 1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = duo256_low_bin(t, j);
+                    sA[k] = a[j].x;
+                    sA[M - k] = a[j].z;
+                    if (hasB) {
+                        sA[M + 1 + k] = a[j].y;
+                        sA[M + 1 + M - k] = a[j].w;
+                    }
+                }
+                if (is0) {
+                    sA[M / 2] = a[8].x;
+                    if (hasB) sA[M + 1 + M / 2] = a[8].y;
+                }
+            }
+        }
     }
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) tm_free_cta<DP::TMEM_COLS>(tacc, tid);
+#endif
     if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
         __syncthreads();
         if (tid == 0) {

@@ -215,13 +215,14 @@ inline void plan_pair_units(const StftArgs& a, long long resident_warps, int uni
 // round-robin is balanced when the units fill the resident lane groups a whole number of times.
 // Fewest rounds x (rows + 1 for the start-up of a unit) wins, fewer blocks (less partial-sum
 // traffic) break ties.  Returns the number of blocks (<= max_blocks).
-// `pair_units`: the units of the staged-sample pair kernel's SUM mode (b2s_pair_kernel.cuh) -- one pair of
-// frames per WARP, so the units per block need not be even.
+// `duos_per_warp`: the lane groups of a warp walk the same sweep block, so the units per block are rounded up
+// to a multiple of it -- 2 for the 512-point frame-duo kernel, 4 for the 256-point one (b2s_duo256_kernel.cuh),
+// 1 for the SUM mode of the staged-sample pair kernel (b2s_pair_kernel.cuh: one pair of frames per warp).
 inline int plan_stft_sum(const StftArgs& a, long long resident_groups, int max_blocks, StftParams& p,
-                         std::string& err, bool pair_units = false) {
+                         std::string& err, int duos_per_warp = 2) {
     const int log2n = plan_stft(a, 1, resident_groups, p, err, false);
     if (log2n < 0) return log2n;
-    const long long nduos = (a.nframes + 1) / 2, ups = pair_units ? nduos : (nduos + 1) / 2 * 2;
+    const long long nduos = (a.nframes + 1) / 2, ups = (nduos + duos_per_warp - 1) / duos_per_warp * duos_per_warp;
     if (resident_groups < 1) resident_groups = 1;
     long long best_cost = -1, best_rows = a.batch > 0 ? a.batch : 1;
     for (long long nb = 1; nb <= max_blocks && nb <= a.batch; ++nb) {

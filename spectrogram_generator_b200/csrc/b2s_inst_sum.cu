@@ -23,6 +23,23 @@ const void* pair_sum_kernel_for(int x_is_f64, int acc_tmem) {
     return acc_tmem ? (const void*)stft_psd_pair_sum_kernel<10, float, 2> : (const void*)stft_psd_pair_sum_kernel<10, float, 1>;
 }
 
+// the SUM mode of the 256-point frame-duo kernel (b2s_duo256_kernel.cuh)
+template <typename Tin, int TM>
+static const void* pick256(int slots) {
+    switch (slots) {
+        case 2: return (const void*)stft_psd_duo256_sum_kernel<Tin, 2, TM>;
+        case 4: return (const void*)stft_psd_duo256_sum_kernel<Tin, 4, TM>;
+        case 8: return (const void*)stft_psd_duo256_sum_kernel<Tin, 8, TM>;
+        case 16: return (const void*)stft_psd_duo256_sum_kernel<Tin, 16, TM>;
+        default: return nullptr;
+    }
+}
+
+const void* duo256_sum_kernel_for(int x_is_f64, int slots, int acc_tmem) {
+    if (x_is_f64) return acc_tmem ? pick256<double, 2>(slots) : pick256<double, 1>(slots);
+    return acc_tmem ? pick256<float, 2>(slots) : pick256<float, 1>(slots);
+}
+
 const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem) {
     if (x_is_f64) return acc_tmem ? pick<double, 1>(slots) : pick<double, 0>(slots);
     return acc_tmem ? pick<float, 1>(slots) : pick<float, 0>(slots);

@@ -109,6 +109,8 @@ struct CudaLauncher {
 // acc_tmem: running sums in tensor memory (else shared memory)
 const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
 
+// the SUM mode of the 256-point frame-duo kernel, slots = 2 / 4 / 8 / 16 (b2s_inst_sum.cu); nullptr if there is none
+const void* duo256_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
 // the SUM mode of the staged-sample pair kernel, nperseg 1024 (b2s_inst_sum.cu)
 const void* pair_sum_kernel_for(int x_is_f64, int acc_tmem);
 

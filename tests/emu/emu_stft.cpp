@@ -228,7 +228,7 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
         using PP = PairPlan<10>;
         if (!pair_kernel_ok(x, x_is_f64, batch, x_batch_stride, nperseg, hop, frame0)) return -200;
         StftParams p{};
-        const int blocks = plan_stft_sum(a, (long long)grid * (PP::NT / 32), max_blocks, p, err, true);
+        const int blocks = plan_stft_sum(a, (long long)grid * (PP::NT / 32), max_blocks, p, err, 1);
         if (blocks < 0) return blocks;
         std::vector<float> tw;
         make_tables(nperseg, tw);
@@ -241,6 +241,36 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
         const size_t smem = PP::sum_smem_bytes(hop, x_is_f64 ? 8 : 4);
         if (x_is_f64) emu::launch(g, PP::NT, smem, [&] { stft_psd_pair_sum_kernel<10, double, 1>(p); });
         else emu::launch(g, PP::NT, smem, [&] { stft_psd_pair_sum_kernel<10, float, 1>(p); });
+        emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
+        return blocks;
+    }
+    if (nperseg == 256) {
+        // the SUM mode of the 256-point frame-duo kernel (sums in shared memory: the twin of the product's kernel)
+        using DP = Duo256Plan;
+        const int s256 = duo256_sum_slots(a, 8);
+        if (!s256) return -200;
+        StftParams p{};
+        const int blocks = plan_stft_sum(a, (long long)grid * DP::FPC, max_blocks, p, err, 4);
+        if (blocks < 0) return blocks;
+        std::vector<float> tw;
+        make_tables(nperseg, tw);
+        p.tw = reinterpret_cast<const float2*>(tw.data());
+        std::vector<float> part((size_t)blocks * elems, std::nanf(""));
+        p.acc = part.data();
+        const long long need = (p.n_units + DP::FPC - 1) / DP::FPC;
+        const unsigned g = (unsigned)(need < grid ? need : grid);
+        auto run = [&](auto kern) { emu::launch(g, DP::NT, DP::SUM_SMEM, [&] { kern(p); }); };
+        if (x_is_f64) {
+            if (s256 == 2) run(stft_psd_duo256_sum_kernel<double, 2, 1>);
+            else if (s256 == 4) run(stft_psd_duo256_sum_kernel<double, 4, 1>);
+            else if (s256 == 8) run(stft_psd_duo256_sum_kernel<double, 8, 1>);
+            else run(stft_psd_duo256_sum_kernel<double, 16, 1>);
+        } else {
+            if (s256 == 2) run(stft_psd_duo256_sum_kernel<float, 2, 1>);
+            else if (s256 == 4) run(stft_psd_duo256_sum_kernel<float, 4, 1>);
+            else if (s256 == 8) run(stft_psd_duo256_sum_kernel<float, 8, 1>);
+            else run(stft_psd_duo256_sum_kernel<float, 16, 1>);
+        }
         emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
         return blocks;
     }

@@ -271,6 +271,31 @@ def test_sum_fused_pair_kernel(emu, hop, detrend, nframes, batch, grid, max_bloc
     assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused pair 1024/{hop}")
 
 
+@pytest.mark.parametrize("hop,detrend", [(64, "constant"), (32, False), (128, "constant"), (224, "constant"), (256, False), (100, "constant")])
+@pytest.mark.parametrize("nframes,batch,grid,max_blocks", [(9, 5, 1, 64), (6, 9, 2, 4), (1, 3, 1, 2), (15, 2, 3, 1)])
+def test_sum_fused_duo256_kernel(emu, hop, detrend, nframes, batch, grid, max_blocks):
+    """nperseg 256: the SUM mode of the 256-point frame-duo kernel (a lane group keeps one duo and walks over a
+    block of sweeps; four duos per warp share the block): rows bit-identical to the per-sweep kernel's -- also at
+    the hops whose per-sweep kernel is the S = 14 / 16 variant -- and the sum equals the float64 sum of the rows
+    to fp32 rounding whatever the split into sweep blocks; float64 samples likewise."""
+    n = 256 + hop * (nframes - 1) + 4
+    x = signal(batch, n, hop + nframes + batch, dc=-2.0 if detrend else 0.0)
+    kw = dict(window=("tukey", 0.25), nperseg=256, noverlap=256 - hop, detrend=detrend)
+    plan = plan_for(n, 20000.0, **kw)
+    assert plan.nframes == nframes
+    rows = emu.stft_psd(x, plan, chunk=2)
+    assert emu.last_family() == "duo256"
+    got, tot, blocks = emu.stft_psd_sum(x, plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert 1 <= blocks <= min(max_blocks, batch)
+    assert np.array_equal(got, rows)
+    want = 0.5 * rows.astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(tot, want, rtol=1e-6, atol=0)
+    got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert np.array_equal(got64, rows) and np.array_equal(tot64, tot)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused duo256 256/{hop}")
+
+
 def test_sum_fused_plan_fills_the_grid():
     """plan_stft_sum on BASELINE config 2 with a B200's resident groups: one round, 22 blocks of 46."""
     import ctypes

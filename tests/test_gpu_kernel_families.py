@@ -209,7 +209,10 @@ def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg,
     (512, 128, 37, 10, 0), (512, 64, 5, 7, 0), (512, 256, 130, 6, 0), (512, 128, 2, 1, 0),
     (512, 128, 9, 8, 1),            # odd row length: rows only 4-byte aligned -> two-pass path inside the library
     (512, 128, 1, 12, 0),           # one sweep
-    (1024, 256, 40, 9, 0), (256, 64, 300, 11, 0), (600, 150, 7, 5, 0), (512, 448, 20, 6, 0),   # no fused kernel for these shapes
+    (1024, 256, 40, 9, 0), (600, 150, 7, 5, 0), (512, 448, 20, 6, 0),   # no fused kernel for these shapes
+    # nperseg 256: the SUM mode of the 256-point frame-duo kernel (S = 2 / 4 / 8, and S = 16 for every other even hop)
+    (256, 64, 300, 11, 3), (256, 64, 1000, 622, 3), (256, 32, 77, 40, 3), (256, 128, 1000, 9, 3), (256, 224, 50, 9, 3),
+    (256, 100, 20, 7, 3), (256, 256, 3, 1, 3),
     # nperseg 1024, rows 16-byte aligned: the SUM mode of the staged-sample pair kernel, any staged hop
     (1024, 256, 1000, 153, 2),      # the north-star target shape (1000 x 40 000 @ 1024/256) with its mean
     (1024, 896, 33, 7, 2), (1024, 1024, 64, 5, 2), (1024, 36, 9, 20, 2), (1024, 256, 2, 1, 2), (1024, 128, 300, 31, 2),
@@ -219,7 +222,7 @@ def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
     the sum equals the float64 sum of the rows to fp32 rounding and is the same on every run;
     float64 samples and a caller-provided flat sum buffer likewise."""
     rng = np.random.default_rng(nperseg + hop + B)
-    n = nperseg + hop * (nfr - 1) + {0: 2, 1: 3, 2: 4}[odd]
+    n = nperseg + hop * (nfr - 1) + {0: 2, 1: 3, 2: 4, 3: 2}[odd]
     x = _signal(rng, B, n, dc=-3.0)
     plan = sg.triage(n, 20000.0, "hann", nperseg, nperseg - hop, None, "constant", True, "density", "psd")
     assert plan.nframes == nfr
@@ -230,6 +233,8 @@ def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
     from spectrogram_generator_b200 import _lib
     if odd == 2:
         assert _lib.last_kernel().startswith("stft_psd_pair_sum_kernel")
+    if odd == 3:
+        assert _lib.last_kernel().startswith("stft_psd_duo256_sum_kernel")
     assert torch.equal(S, rows)
     want = rows.double().sum(dim=0) / B
     torch.testing.assert_close(tot.double(), want, rtol=2e-6, atol=0)
