@@ -54,8 +54,10 @@ int b2s_set_reserved_sms(int n);
 /* Diagnostic switches of the kernel selection.  Their defaults come from the
  * B2S_* environment variables, read ONCE at the first call into the library (never on the per-call
  * path); this entry changes one at run time: "no_duo", "duo1024", "no_duo4", "no_big", "no_pair",
- * "static_units", "no_fused_sum", "sum_acc_smem" (value 0 / 1) and "pair_units" (work units per
- * resident warp of the staged-sample kernel, 0 = default).  Not needed in normal use; the GPU tests
+ * "no_pairq", "no_mixed", "static_units", "no_fused_sum", "sum_acc_smem", "sum_dynamic" (value 0 / 1),
+ * "pair_units" (work units per resident warp of the staged-sample kernel), "pair_nt" (its CTA width),
+ * "sum_blocks" (sweep blocks of the sum-fused kernels) and "peer_timeout_ms" -- 0 = default each.
+ * Not needed in normal use; the GPU tests
  * use it to compare kernel variants bit for bit.  Returns B2S_OK or B2S_ERR_BAD_ARG.  (No
  * counterpart in the reference.) */
 int b2s_set_option(const char* name, int value);
@@ -183,10 +185,12 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
  *               (sweep order inside a block of sweeps, then block order)
  *   scratch     device, b2s_stft_psd_sum_scratch_elems(batch, nframes*(nperseg/2+1)) floats
  *
- * For nperseg 512 with hop 64 / 128 / 256 one kernel walks a frame pair over a block of
- * sweeps and keeps the running sums on chip, so the [batch][nframes][bins] result is written
- * once and never read back; every other shape runs b2s_stft_psd_* followed by
- * b2s_batch_sum_f32.  The per-sweep rows are bit-identical to b2s_stft_psd_*'s either way.
+ * For nperseg 512 with hop 64 / 128 / 256, nperseg 256 with any even hop and nperseg 1024 with
+ * any hop that is a multiple of 4 (rows and window 16-byte aligned) one kernel walks a frame
+ * pair over a block of sweeps and keeps the running sums on chip (tensor memory), so the
+ * [batch][nframes][bins] result is written once and never read back; every other shape runs
+ * b2s_stft_psd_* followed by b2s_batch_sum_f32.  The per-sweep rows are bit-identical to
+ * b2s_stft_psd_*'s either way.
  */
 long long b2s_stft_psd_sum_scratch_elems(long long batch, long long elems);
 int b2s_stft_psd_sum_f32(const float* x, long long batch, long long n, long long x_batch_stride,

@@ -149,6 +149,8 @@ struct EnvSwitches {
     bool allow_pair = true, allow_pairq = false, fused_sum = true, sum_acc_smem = false, allow_mixed = true;
     int pair_units = 0;          // B2S_PAIR_UNITS: work units per resident warp of the pair kernel (0: default)
     int pair_nt = 0;             // B2S_PAIR_NT: threads per CTA of the pair kernel (0: default)
+    int sum_blocks = 0;          // B2S_SUM_BLOCKS: sweep blocks of the sum-fused kernels (0: plan_stft_sum's choice)
+    bool sum_dynamic = false;    // B2S_SUM_DYNAMIC: the sum-fused kernels draw their units from an atomic counter
     int peer_timeout_ms = 0;     // B2S_PEER_TIMEOUT_MS: how long the peer all-reduce waits for a late rank (0: 120 s)
     EnvSwitches() {
         auto on = [](const char* name) { const char* v = getenv(name); return v && atoi(v) != 0; };
@@ -167,6 +169,8 @@ struct EnvSwitches {
         sum_acc_smem = on("B2S_SUM_ACC_SMEM");
         if (const char* v = getenv("B2S_PAIR_UNITS")) pair_units = atoi(v);
         if (const char* v = getenv("B2S_PAIR_NT")) pair_nt = atoi(v);
+        if (const char* v = getenv("B2S_SUM_BLOCKS")) sum_blocks = atoi(v);
+        sum_dynamic = on("B2S_SUM_DYNAMIC");
         if (const char* v = getenv("B2S_PEER_TIMEOUT_MS")) peer_timeout_ms = atoi(v);
     }
 };
@@ -463,6 +467,23 @@ constexpr int kMaxSumBlocks = 64;       // sweep blocks of the sum-fused kernel:
 
 // the sum-fused frame-duo kernel (per-sweep rows and their cross-sweep sum in one pass), then the
 // fold over its sweep blocks.  Static schedule: plan_stft_sum makes the units fill the grid evenly.
+// diagnostic overrides of plan_stft_sum's choice (b2s_set_option "sum_blocks" / "sum_dynamic")
+int apply_sum_overrides(const b2s::StftArgs& a, int blocks, int dev, cudaStream_t stream, b2s::StftParams& p) {
+    if (env().sum_blocks > 0) {
+        long long nb = env().sum_blocks < kMaxSumBlocks ? env().sum_blocks : kMaxSumBlocks;
+        if (nb > a.batch) nb = a.batch;
+        const long long rows = (a.batch + nb - 1) / nb;
+        blocks = (int)((a.batch + rows - 1) / rows);
+        p.acc_rows = (int)rows;
+        p.n_units = (long long)blocks * p.units_per_signal;
+    }
+    if (env().sum_dynamic && !stream_capturing(stream)) {
+        const int rc = work_counters(dev, stream, &p.work);
+        if (rc != B2S_OK) return rc;
+    }
+    return blocks;
+}
+
 struct SumKernelShape {
     const void* kern;        // the launch's kernel (running sums in tensor memory, or the twin)
     const void* twin;        // the shared-memory twin: residency is taken from it
@@ -503,9 +524,11 @@ int launch_sum_kernel(const b2s::StftArgs& a, const SumKernelShape& ks_in, float
     const long long resident_ctas = (long long)(di.sm_count - reserve) * occ;
     b2s::StftParams p{};
     std::string err;
-    const int blocks = b2s::plan_stft_sum(a, resident_ctas * ks_in.fpc, kMaxSumBlocks, p, err, ks_in.duos_per_warp);
+    int blocks = b2s::plan_stft_sum(a, resident_ctas * ks_in.fpc, kMaxSumBlocks, p, err, ks_in.duos_per_warp);
     if (blocks < 0) return fail(blocks, err);
     if (p.n_units == 0) return B2S_OK;
+    blocks = apply_sum_overrides(a, blocks, dev, stream, p);
+    if (blocks < 0) return blocks;
     p.acc = scratch;
     rc = twiddles(dev, a.nperseg, false, &p.tw);
     if (rc != B2S_OK) return rc;
@@ -590,9 +613,11 @@ int launch_pair_sum(const b2s::StftArgs& a, float* sum_out, float post_scale, fl
     int occ_plan = 3;
     while (occ_plan > 1 && (long long)occ_plan * (PP::smem_bytes(a.hop, 4, PP::NT) + 1024) > (long long)di.smem_optin + 1024) --occ_plan;
     const long long plan_groups = (long long)(di.sm_count - reserve) * occ_plan * fpc;
-    const int blocks = b2s::plan_stft_sum(a, plan_groups, kMaxSumBlocks, p, err, 1);
+    int blocks = b2s::plan_stft_sum(a, plan_groups, kMaxSumBlocks, p, err, 1);
     if (blocks < 0) return fail(blocks, err);
     if (p.n_units == 0) return B2S_OK;
+    blocks = apply_sum_overrides(a, blocks, dev, stream, p);
+    if (blocks < 0) return blocks;
     p.acc = scratch;
     p.ring = PP::ring_samples(a.hop);
     rc = twiddles(dev, a.nperseg, false, &p.tw);
@@ -700,6 +725,8 @@ int b2s_set_option(const char* name, int value) {
     else if (n == "sum_acc_smem") e.sum_acc_smem = on;
     else if (n == "pair_units") e.pair_units = value;
     else if (n == "pair_nt") e.pair_nt = value;
+    else if (n == "sum_blocks") e.sum_blocks = value;
+    else if (n == "sum_dynamic") e.sum_dynamic = on;
     else if (n == "peer_timeout_ms") e.peer_timeout_ms = value;
     else return fail(B2S_ERR_BAD_ARG, "b2s_set_option: unknown option " + n);
     return B2S_OK;

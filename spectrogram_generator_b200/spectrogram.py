@@ -200,9 +200,10 @@ class Engine:
         """Per-sweep spectrograms and their cross-sweep sum in one pass (BASELINE config 2).
         x: CUDA tensor [B, n]; returns ``(S[B, nframes, nbins], post_scale * S.sum(0))`` -- the
         rows are bit-identical to :meth:`stft_psd`'s, the sum is added in a fixed order.  For the
-        shapes of the sum-fused kernel (nperseg 512, hop 64/128/256) the rows are written once and
-        never read back; other shapes run :meth:`stft_psd` followed by :meth:`batch_sum` inside
-        the library.  ``sum_out``: any contiguous CUDA float32 tensor of nframes*nbins elements."""
+        shapes of the sum-fused kernels (nperseg 512 with hop 64/128/256, nperseg 256 with any even
+        hop, nperseg 1024 with any hop that is a multiple of 4) the rows are written once and never
+        read back; other shapes run :meth:`stft_psd` followed by :meth:`batch_sum` inside the
+        library.  ``sum_out``: any contiguous CUDA float32 tensor of nframes*nbins elements."""
         lib = _lib.load()
         if x.dim() != 2 or not x.is_cuda or x.dtype not in (torch.float32, torch.float64):
             raise ValueError("stft_psd_sum expects a CUDA float32/float64 tensor of shape [batch, n]")

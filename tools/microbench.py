@@ -132,6 +132,17 @@ def main():
                    (1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 256, 64)]:
             for fused in (True, False):
                 print(json.dumps(time_mean(*sh, flush=flush, fused=fused)), flush=True)
+    if args.set == "meandyn":       # the sum-fused kernels: sweep blocks and static / dynamic unit schedule
+        from spectrogram_generator_b200 import _lib
+        for sh in [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 256, 64)]:
+            for blocks, dyn in [(0, 0), (0, 1), (33, 1), (44, 1), (64, 1), (44, 0), (64, 0)]:
+                _lib.set_option("sum_blocks", blocks)
+                _lib.set_option("sum_dynamic", dyn)
+                r = time_mean(*sh, flush=flush)
+                r.update(sum_blocks=blocks, sum_dynamic=dyn)
+                print(json.dumps(r), flush=True)
+        _lib.set_option("sum_blocks", 0)
+        _lib.set_option("sum_dynamic", 0)
     if args.set == "mean1024":      # one shape, for ncu
         print(json.dumps(time_mean(1000, 40000, 1024, 256, iters=3, flush=flush)), flush=True)
     for s in shapes:
