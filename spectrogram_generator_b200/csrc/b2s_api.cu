@@ -659,9 +659,12 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
                                        : "stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
         return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
     }
-    if (env().fused_sum && env().allow_duo && env().allow_pair && batch >= 2 &&
-        b2s::pair_kernel_ok(x, (int)(sizeof(Tin) == 8), batch, x_batch_stride, nperseg, hop, frame0) &&
-        reinterpret_cast<uintptr_t>(window) % 16 == 0) {
+    b2s::CudaLauncher Lsel{(cudaStream_t)stream};
+    Lsel.allow_duo = env().allow_duo;
+    Lsel.duo1024 = env().duo1024;
+    Lsel.allow_duo4 = env().allow_duo4;
+    Lsel.allow_pair = env().allow_pair && env().allow_duo;
+    if (env().fused_sum && batch >= 2 && b2s::pair_preferred(a, Lsel)) {
         b2s_note_kernel("stft_psd_pair_sum_kernel (staged samples, running cross-sweep sums in tensor memory) + fold", a);
         return launch_pair_sum(a, sum_out, post_scale, scratch, (cudaStream_t)stream);
     }

@@ -144,6 +144,26 @@ int dispatch_duo_big(const StftArgs& a, Launcher& L) {
     return L.template duo_cta<LOG2N, Tin, MODE>(a);
 }
 
+// nperseg 1024: does this call take the staged-sample pair kernel (b2s_pair_kernel.cuh)?  Any hop that keeps
+// the frames 16-byte aligned -- except float64 samples at the four-step kernel's overlapping hops (128, 256,
+// 512): there every frame re-reads and re-converts its staged doubles (two trips, 64 LDS.128 and 128 F2F per
+// lane and frame, and the double ring leaves room for two CTAs per SM instead of three), while the frame-duo
+// kernel converts each sample once on its way into the sliding register window.  Measured on B200
+// (tools/microbench.py --set n1024x --dtype f64, 1000 x 40 000): hop 256 0.324 -> 0.201 ms, hop 512 0.160 ->
+// 0.125, hop 128 (1024 x 100 000) 1.350 -> 0.853; from hop 896 up the pair kernel is level or ahead and stays.
+// (Also used by the sum-fused entry: its rows must come from the same per-frame code as b2s_stft_psd_*'s.)
+template <class Launcher>
+bool pair_preferred(const StftArgs& a, const Launcher& L) {
+    if (!L.allow_pair || !pair_kernel_ok(a.x, a.x_is_f64, a.batch, a.x_batch_stride, a.nperseg, a.hop, a.frame0) ||
+        reinterpret_cast<uintptr_t>(a.window) % 16 != 0)
+        return false;
+    if (a.x_is_f64 && L.allow_duo && L.duo1024 && L.allow_duo4 && a.hop <= 512) {
+        const int s4 = duo4_slots(a);
+        if (s4 == 2 || s4 == 4 || s4 == 8) return false;
+    }
+    return true;
+}
+
 // staged-sample kernel for nperseg 2048 .. 16384 (b2s_pairq_kernel.cuh): 16-byte aligned frames
 template <class Launcher>
 bool pairq_ok(const StftArgs& a, const Launcher& L) {
@@ -164,9 +184,7 @@ int dispatch_tg(const StftArgs& a, Launcher& L) {
         case 9: return dispatch_warp_shift<9, Tin, MODE>(a, L, shift);
         case 10:
             // staged-sample pair kernel: any hop that keeps the frames 16-byte aligned
-            if (L.allow_pair && pair_kernel_ok(a.x, a.x_is_f64, a.batch, a.x_batch_stride, a.nperseg, a.hop, a.frame0) &&
-                reinterpret_cast<uintptr_t>(a.window) % 16 == 0)
-                return L.template pair<10, Tin, MODE>(a);
+            if (pair_preferred(a, L)) return L.template pair<10, Tin, MODE>(a);
             if (L.allow_duo && L.duo1024) return dispatch_duo_big<10, Tin, MODE>(a, L);
             return dispatch_warp_shift<10, Tin, MODE>(a, L, shift);
         case 11:

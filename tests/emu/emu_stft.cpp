@@ -226,7 +226,10 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
         // the SUM mode of the staged-sample pair kernel (sums in shared memory: the twin of the product's
         // tensor-memory kernel), `grid` resident CTAs of four warps
         using PP = PairPlan<10>;
-        if (!pair_kernel_ok(x, x_is_f64, batch, x_batch_stride, nperseg, hop, frame0)) return -200;
+        {
+            EmuLauncher Lsel{};
+            if (!pair_preferred(a, Lsel)) return -200;      // (as the library: float64 at hop 128 / 256 / 512 has no fused kernel)
+        }
         StftParams p{};
         const int blocks = plan_stft_sum(a, (long long)grid * (PP::NT / 32), max_blocks, p, err, 1);
         if (blocks < 0) return blocks;

@@ -264,9 +264,10 @@ def test_sum_fused_pair_kernel(emu, hop, detrend, nframes, batch, grid, max_bloc
     assert np.array_equal(got, rows)
     want = 0.5 * rows.astype(np.float64).sum(axis=0)
     np.testing.assert_allclose(tot, want, rtol=1e-6, atol=0)
-    got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
-    assert np.array_equal(got64, emu.stft_psd(x.astype(np.float64), plan, chunk=2))
-    np.testing.assert_allclose(tot64, want, rtol=2e-6, atol=0)
+    if hop not in (128, 256, 512):      # float64 samples at these hops take the four-step frame-duo kernel: no fused form
+        got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+        assert np.array_equal(got64, emu.stft_psd(x.astype(np.float64), plan, chunk=2))
+        np.testing.assert_allclose(tot64, want, rtol=2e-6, atol=0)
     _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
     assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused pair 1024/{hop}")
 
@@ -368,7 +369,16 @@ def test_four_step_duo_kernel(emu, nperseg, hop, detrend, pair, monkeypatch):
     b = emu.stft_psd(x, plan, chunk=2, grid=2)
     assert_parity(a, So, what=f"{emu.last_family()} {nperseg}/{hop}")
     assert np.array_equal(a, b)
-    if not (pair and nperseg == 16384):      # (a float64 ring of 16384 samples does not fit: float64 takes the round-1 kernel)
+    if pair and nperseg == 1024 and hop in (128, 256, 512):
+        # float64 samples at the overlapping hops take the four-step frame-duo kernel (every frame of the staged
+        # kernel would re-convert its doubles): the same bits as that kernel gives float samples
+        a64 = emu.stft_psd(x.astype(np.float64), plan, chunk=4)
+        assert emu.last_family() == "duo4"
+        monkeypatch.setenv("B2S_NO_PAIR", "1")
+        assert np.array_equal(a64, emu.stft_psd(x, plan, chunk=3))
+        monkeypatch.delenv("B2S_NO_PAIR")
+        assert_parity(a64, So, what=f"duo4 float64 {nperseg}/{hop}")
+    elif not (pair and nperseg == 16384):    # (a float64 ring of 16384 samples does not fit: float64 takes the round-1 kernel)
         assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, chunk=4), a)
     part = emu.stft_psd(x, plan, kmin=3, kmax=500, frame0=1, nframes=nfr - 2, chunk=4)
     assert np.array_equal(part, a[:, 1:nfr - 1, 3:501])
@@ -391,7 +401,8 @@ def test_pair_kernel_cta_shapes(emu, nt, hop, detrend, monkeypatch):
     monkeypatch.setenv("B2S_PAIR_NT", str(nt))
     b = emu.stft_psd(x, plan, grid=1)
     assert np.array_equal(a, b)
-    assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, grid=1), a)
+    if hop not in (128, 256, 512):      # (float64 samples at these hops take the four-step frame-duo kernel)
+        assert np.array_equal(emu.stft_psd(x.astype(np.float64), plan, grid=1), a)
 
 
 @pytest.mark.parametrize("nperseg,hop", [(1000, 875), (288, 72), (260, 65), (2000, 500), (8000, 2000), (315, 100), (1001, 300),

@@ -83,7 +83,9 @@ def time_mean(batch, n, nperseg, hop, iters=10, flush=None, fused=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="core")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="sample type of the device-resident input")
     args = ap.parse_args()
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
     flush = None if os.environ.get("B2S_MB_NOFLUSH") == "1" else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     shapes = []
     if args.set in ("core", "all"):
@@ -147,7 +149,12 @@ def main():
         print(json.dumps(time_mean(1000, 40000, 1024, 256, iters=3, flush=flush)), flush=True)
     for s in shapes:
         kw = {"window": s[4]} if len(s) > 4 else {}
-        print(json.dumps(time_shape(*s[:4], flush=flush, **kw)), flush=True)
+        r = time_shape(*s[:4], flush=flush, dtype=dtype, **kw)
+        from spectrogram_generator_b200 import _lib
+        r["kernel"] = _lib.last_kernel().split(" (")[0]
+        if args.dtype == "f64":
+            r["dtype"] = "f64"
+        print(json.dumps(r), flush=True)
 
 
 if __name__ == "__main__":
