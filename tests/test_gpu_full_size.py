@@ -44,6 +44,33 @@ def test_config2_all_1000_sweeps_and_the_mean():
     assert np.max(np.abs(m[big] - mean64[big]) / mean64[big]) <= 1e-5       # averaging 1000 sweeps: far inside the bar
 
 
+@pytest.mark.parametrize("nperseg", [1024, 256])
+def test_config2_sweeps_at_the_other_fused_lengths_and_their_mean(nperseg):
+    """The config-2 batch (1000 sweeps x 40 000 samples) at nperseg 1024 / hop 256 -- the north-star target shape
+    -- and 256 / 64, through mean_spectrogram: per-sweep rows AND the mean come from the sum-fused kernels of
+    round 2 (SUM mode of the staged-sample pair kernel / of the 256-point frame-duo kernel).  Every row against
+    the float64 oracle with SciPy-float32 beside it, the mean against the float64 mean."""
+    from spectrogram_generator_b200 import _lib
+    x, kw = synth.config2(batch=1000)
+    fs = kw.pop("fs")
+    kw.update(nperseg=nperseg, noverlap=nperseg - nperseg // 4)
+    f, t, m, S = sg.mean_spectrogram(x, fs=fs, return_per_sweep=True, **kw)
+    assert "_sum_kernel" in _lib.last_kernel(), _lib.last_kernel()
+    st = FullSizeStats(f"C2 batch @ {nperseg}/{nperseg // 4}")
+    mean64 = np.zeros(S.shape[1:])
+    for lo in range(0, 1000, 100):
+        fo, to, So = scipy.signal.spectrogram(x[lo:lo + 100].astype(np.float64), fs=fs, **kw)
+        S32 = scipy.signal.spectrogram(x[lo:lo + 100], fs=fs, **kw)[2]
+        assert np.array_equal(f, fo) and np.array_equal(t, to)
+        st.add(S[lo:lo + 100], So, S32)
+        mean64 += So.sum(axis=0)
+    st.check()
+    mean64 /= 1000
+    assert np.max(np.abs(m - mean64)) <= 1e-6 * mean64.max()
+    big = mean64 >= 1e-6 * mean64.max()
+    assert np.max(np.abs(m[big] - mean64[big]) / mean64[big]) <= 1e-5
+
+
 def test_config4_sixteen_channels_sixty_seconds():
     x, kw = synth.config4(seconds=60.0)
     fs = kw.pop("fs")
