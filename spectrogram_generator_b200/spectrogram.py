@@ -397,6 +397,7 @@ def _to_host(d: torch.Tensor, dtype) -> np.ndarray:
 
 
 _PIPE_CHUNK_BYTES = 32 << 20       # output bytes per pipeline stage
+_PIPE_RAMP_DIV = 16                # the first stage is 1/_PIPE_RAMP_DIV of a full one, the next ones double
 
 
 class _Streams:
@@ -460,7 +461,7 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
             # chunks are small (1/16 of a stage, doubling), so the D2H stream idles for ~0.05 ms instead of a
             # full stage's copy-in + compute
             step = max(1, _PIPE_CHUNK_BYTES // row_bytes)
-            b, cur_step = 0, max(1, step // 16)
+            b, cur_step = 0, max(1, step // _PIPE_RAMP_DIV)
             while b < B:
                 items.append((b, min(B, b + cur_step), 0, F))
                 b += cur_step
@@ -468,7 +469,7 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
         else:
             fstep = max(1, _PIPE_CHUNK_BYTES // (kout * 4))
             for b in range(B):
-                f, cur_step = 0, max(1, fstep // 16)
+                f, cur_step = 0, max(1, fstep // _PIPE_RAMP_DIV)
                 while f < F:
                     items.append((b, b + 1, f, min(F, f + cur_step)))
                     f += cur_step
