@@ -19,7 +19,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .spectrogram import _prepare_input, _to_device, _to_host, engine, triage
+from .spectrogram import _as_host_tensor, _prepare_input, _to_device, _to_host, engine, triage
 from .windows import rfftfreq, time_axis
 
 DEFAULT_BANDS = {
@@ -51,6 +51,17 @@ class SpectrogramPath:
         self.last_Sxx = None
         self.segment_map = []
         self._last_Sxx_dev = None
+        self._combined = None            # (host array returned by combine(), its copy on the device)
+
+    def _dev(self):
+        return torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+
+    def _device_row(self, data, x, dev):
+        """The 1-D signal as a [1, n] device tensor.  The array combine() returned was assembled on the device
+        sweep by sweep while the host concatenated: it is not uploaded a second time."""
+        if self._combined is not None and data is self._combined[0] and self._combined[1].device == dev:
+            return self._combined[1].reshape(1, -1)
+        return _to_device(x.reshape(1, -1), dev)
 
     # -- the call at PlotEngine.py:113 / :232, with the band mask fused as a crop --
     def _spectrogram_cropped(self, data, fs, nperseg, fmin, fmax):
@@ -67,10 +78,9 @@ class SpectrogramPath:
             return f[:0], t, np.empty((0, plan.nframes), dtype=out_dtype)
         eng = engine()
         eng.require_cuda()
-        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None \
-            else torch.device(self.device)
+        dev = self._dev()
         with torch.cuda.device(dev):
-            xd = _to_device(x.reshape(1, -1), dev)
+            xd = self._device_row(data, x, dev)
             Sd = eng.stft_psd(xd, plan, kmin=bins[0], kmax=bins[1])
             self._last_Sxx_dev = Sd[0]                       # [frame][bin], kept for the display scaling
             S = _to_host(Sd[0], out_dtype)
@@ -134,7 +144,7 @@ class SpectrogramPath:
                 else torch.device(self.device)
             with torch.cuda.device(dev):
                 # fused epilogue: only F numbers leave the kernel (no [F][K] spectrogram)
-                band = eng.band_power(_to_device(x.reshape(1, -1), dev), plan, bins[0], bins[1])
+                band = eng.band_power(self._device_row(signal, x, dev), plan, bins[0], bins[1])
                 power_feature = _to_host(band[0], out_dtype)
         log_power = np.log10(power_feature + 1e-20)
         delta_log_power = np.diff(log_power, prepend=log_power[0])
@@ -178,7 +188,12 @@ class SpectrogramPath:
 
     def combine(self, sweeps_info, settings):
         """'Combine all sweeps': time concatenation with a segment map
-        (PlotEngine.py:162-200).  Returns the concatenated signal."""
+        (PlotEngine.py:162-200).  Returns the concatenated signal (the reference plots it as the trace).
+        When a GPU is there the sweeps are also copied, one by one, to their offsets in ONE device buffer
+        (asynchronously where they are page-locked, beside the host's ``np.concatenate``); handing the returned
+        array to ``_plot_spectrogram`` / ``_calculate_features`` then uses that buffer instead of uploading the
+        concatenated signal again.  Same samples, same kernels: bit-identical to the upload."""
+        self._combined = None
         self.segment_map = []
         offset, parts = 0.0, []
         use_proc = settings.get("draw_proc", True)
@@ -194,4 +209,23 @@ class SpectrogramPath:
                                      "source_item": info.get("item")})
             parts.append(sig)
             offset += duration
-        return np.concatenate(parts) if parts else None
+        if not parts:
+            return None
+        staged = None
+        if torch.cuda.is_available():
+            arrs = [np.asarray(q) for q in parts]
+            dt = np.result_type(*arrs)
+            if dt in (np.float32, np.float64) and all(a.ndim == 1 for a in arrs):
+                dev = self._dev()
+                total = sum(a.shape[0] for a in arrs)
+                with torch.cuda.device(dev):
+                    staged = torch.empty((total + (total & 1),), dtype=torch.from_numpy(np.empty(0, dt)).dtype, device=dev)[:total]
+                    at = 0
+                    for a in arrs:
+                        h = _as_host_tensor(np.ascontiguousarray(a, dtype=dt))
+                        staged[at:at + a.shape[0]].copy_(h, non_blocking=h.is_pinned())
+                        at += a.shape[0]
+        final = np.concatenate(parts)
+        if staged is not None:
+            self._combined = (final, staged)
+        return final

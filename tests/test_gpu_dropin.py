@@ -116,6 +116,41 @@ def test_plot_extra_source_selection_and_combine():
     assert np.max(np.abs(img - ref["image"])) <= 1e-4
 
 
+def test_combine_assembles_the_sweeps_on_the_device():
+    """combine() copies the sweeps one by one to their offsets in one device buffer; the
+    spectrogram / features of the array it returns use that buffer (no second upload of the concatenated
+    signal) and are bit-identical to the plain upload.  Sweeps of unequal length, an odd total, mixed
+    float32 / float64 (np.concatenate promotes), and a stale buffer is never used for another array."""
+    import torch
+    a, fs = sweep(seed=5)
+    b, _ = sweep(seed=6)
+    c, _ = sweep(seed=7)
+    settings = dict(nperseg=256, fmin=1.0, fmax=300.0, log_scale=True, mode_proc="None", mode_raw="Both",
+                    draw_proc=False, draw_raw=True)
+    for parts in ([a, b[:-1777], c[:12345]], [a.astype(np.float64), b, c[:999]]):
+        infos = [dict(signal_raw=q, signal_proc=None, fs=fs, item=i) for i, q in enumerate(parts)]
+        path = sg.SpectrogramPath()
+        cat = path.combine(infos, settings)
+        want, seg = stft_oracle.combine_sweeps(parts, [fs] * len(parts))
+        assert np.array_equal(cat, want) and cat.dtype == want.dtype
+        assert path._combined is not None and path._combined[0] is cat
+        assert torch.equal(path._combined[1].cpu(), torch.from_numpy(want))
+        img = path.plot_extra(cat, None, fs, settings)
+        t1, feat1 = path._calculate_features(cat, fs, settings)
+        plain = sg.SpectrogramPath()                         # the same array without the device copy
+        img0 = plain.plot_extra(want.copy(), None, fs, settings)
+        t0, feat0 = plain._calculate_features(want.copy(), fs, settings)
+        assert np.array_equal(path.last_Sxx, plain.last_Sxx) and np.array_equal(img, img0)
+        assert np.array_equal(t1, t0) and np.array_equal(feat1, feat0)
+        ref = reference_path.plot_spectrogram_compute(want.astype(np.float64), fs, settings)
+        assert_parity(path.last_Sxx, ref["last_Sxx"])
+        # another array of the same length does not pick the staged buffer up
+        other = want[::-1].copy()
+        path.plot_extra(other, None, fs, settings)
+        plain.plot_extra(other.copy(), None, fs, settings)
+        assert np.array_equal(path.last_Sxx, plain.last_Sxx)
+
+
 def test_display_scale_kernel_matches_reference_lines():
     import torch
     rng = np.random.default_rng(11)
