@@ -185,8 +185,9 @@ int b2s_batch_sum_f32(const float* in, long long batch, long long elems, long lo
  *               (sweep order inside a block of sweeps, then block order)
  *   scratch     device, b2s_stft_psd_sum_scratch_elems(batch, nframes*(nperseg/2+1)) floats
  *
- * For nperseg 512 with hop 64 / 128 / 256, nperseg 256 with any even hop and nperseg 1024 with
- * any hop that is a multiple of 4 (rows and window 16-byte aligned) one kernel walks a frame
+ * For nperseg 512 with hop 64 / 128 / 256, nperseg 256 with any even hop, nperseg 1024 with
+ * any hop that is a multiple of 4 (rows and window 16-byte aligned) and nperseg 2048 with hop
+ * 256 / 512 / 1024 one kernel walks a frame
  * pair over a block of sweeps and keeps the running sums on chip (tensor memory), so the
  * [batch][nframes][bins] result is written once and never read back; every other shape runs
  * b2s_stft_psd_* followed by b2s_batch_sum_f32.  The per-sweep rows are bit-identical to

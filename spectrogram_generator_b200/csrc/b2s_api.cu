@@ -552,7 +552,14 @@ int launch_duo_sum(const b2s::StftArgs& a, int slots, float* sum_out, float post
                    cudaStream_t stream) {
     const int tmem = env().sum_acc_smem ? 0 : 1;
     SumKernelShape ks{};
-    if (a.nperseg == 256) {
+    if (a.nperseg == 2048) {
+        // (the tensor-memory kernel is launched without the twin's shared-memory sums)
+        using DP = b2s::Duo4Plan<11>;
+        ks.twin = b2s::duo4_sum_kernel_for(11, a.x_is_f64, slots, 0);
+        ks.kern = tmem ? b2s::duo4_sum_kernel_for(11, a.x_is_f64, slots, 1) : ks.twin;
+        ks.nt = DP::NT, ks.fpc = DP::FPC, ks.smem = tmem ? DP::SMEM : DP::SUM_SMEM, ks.tmem_cols = DP::TMEM_COLS;
+        ks.duos_per_warp = 1;
+    } else if (a.nperseg == 256) {
         using DP = b2s::Duo256Plan;
         ks.twin = b2s::duo256_sum_kernel_for(a.x_is_f64, slots, 0);
         ks.kern = tmem ? b2s::duo256_sum_kernel_for(a.x_is_f64, slots, 1) : ks.twin;
@@ -654,9 +661,16 @@ int stft_sum_entry(const Tin* x, long long batch, long long n, long long x_batch
     int slots = (!env().fused_sum || !env().allow_duo || batch < 2) ? 0 : b2s::duo_slots(a, b2s::ilog2_exact(nperseg));
     if (slots > 8) slots = 0;           // hop 7/8 nperseg and nperseg: per-sweep frame-duo kernel, no sum-fused variant
     if (nperseg == 256 && env().fused_sum && env().allow_duo && batch >= 2) slots = b2s::duo256_sum_slots(a, 8);
+    // (nperseg 4096: the fused form measured slower than kernel + two-pass sum, b2s_inst_sum4.cu)
+    if (nperseg == 2048 && env().fused_sum && env().allow_duo && env().allow_duo4 && !env().allow_pairq &&
+        batch >= 2) {
+        slots = b2s::duo4_slots(a);         // the per-sweep call takes the four-step frame-duo kernel for these hops
+        if (slots != 2 && slots != 4 && slots != 8) slots = 0;
+    }
     if (slots) {
         b2s_note_kernel(nperseg == 256 ? "stft_psd_duo256_sum_kernel (frame duo, 8 lanes, running cross-sweep sums in tensor memory) + fold"
-                                       : "stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
+                        : nperseg >= 2048 ? "stft_psd_duo4_sum_kernel (four-step frame duo, running cross-sweep sums in tensor memory) + fold"
+                                          : "stft_psd_duo_sum_kernel (frame duo, running cross-sweep sums in tensor memory) + fold", a);
         return launch_duo_sum(a, slots, sum_out, post_scale, scratch, (cudaStream_t)stream);
     }
     b2s::CudaLauncher Lsel{(cudaStream_t)stream};

@@ -15,9 +15,19 @@
 // Against the generic two-pass scheme (b2s_duo_cta_kernel.cuh) this halves the group-wide
 // exchanges and barriers, keeps the raw samples of the overlapping frames in registers (each
 // sample is requested once per run) and reads the pass-1 twiddles once per warp.
+//
+// SUM mode (stft_psd_duo4_sum_kernel, nperseg 2048 / 4096: per-sweep spectrograms AND their cross-sweep sum
+// in one pass): as in b2s_duo_sum_kernel.cuh the thread group keeps ONE frame duo and walks
+// over a block of consecutive sweeps, loading all its 16 + S slots afresh one sweep ahead; rows bit-identical
+// to the per-sweep kernel's.  A thread's final-stage tasks produce 128 / G x 2 R = 16 packed power values
+// (+ bin M/2 in thread 0 of the duo); they are added in sweep order into 34 running sums per thread --
+// tensor memory (SUM = 2, the product path) or shared memory (SUM = 1: emulator / residency twin).
 #pragma once
 
+#include <type_traits>
+
 #include "b2s_duo_cta_kernel.cuh"
+#include "b2s_tmem.cuh"
 
 namespace b2s {
 
@@ -50,6 +60,10 @@ struct Duo4Plan {
     static constexpr int FIN2 = POST_IN_SMEM ? (R - 1) * 256 : 0;
     static constexpr int POST2 = POST_IN_SMEM ? (M + 2) : 0;
     static constexpr size_t SMEM = (size_t)TOTAL * sizeof(float4) + (size_t)(FIN2 + POST2) * sizeof(float2);
+    // SUM mode: packed (A, B) running sums per thread -- TPT tasks x 2 R bins, + bin M/2 (thread 0 of the duo)
+    static constexpr int ACC_SLOTS = TPT * 2 * R + 1;    // 17 float2
+    static constexpr size_t SUM_SMEM = (SMEM + 15) / 16 * 16 + (size_t)ACC_SLOTS * NT * sizeof(float2);
+    static constexpr int TMEM_COLS = 64;                 // 34 used
     static_assert(R == 2 || R == 4 || R == 8, "four-step duo kernel: nperseg 1024, 2048, 4096");
     static_assert(PL::NS == 256 && PL::GF == R, "plan tables");
 };
@@ -76,8 +90,23 @@ B2S_DEVICE float2 duo4_group_sum(float2 v, int grp, int j, float4* red) {
     return v;
 }
 
+template <int LOG2N, typename Tin, int S, int MODE, int SUM>
+B2S_DEVICE void stft_psd_duo4_body(const StftParams& p);
+
 template <int LOG2N, typename Tin, int S, int MODE>
 B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) stft_psd_duo4_kernel(const StftParams p) {
+    stft_psd_duo4_body<LOG2N, Tin, S, MODE, 0>(p);
+}
+// per-sweep rows + cross-sweep block sums (SUM = 1: sums in shared memory, 2: in tensor memory);
+// units: plan_stft_sum(..., duos_per_warp = 1) -- a duo is one or more whole warps
+template <int LOG2N, typename Tin, int S, int SUM>
+B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) stft_psd_duo4_sum_kernel(const StftParams p) {
+    stft_psd_duo4_body<LOG2N, Tin, S, EPI_PLAIN, SUM>(p);
+}
+
+template <int LOG2N, typename Tin, int S, int MODE, int SUM>
+B2S_DEVICE void stft_psd_duo4_body(const StftParams& p) {
+    static_assert(SUM == 0 || MODE == EPI_PLAIN, "SUM mode: plain epilogue");
     using PL = Plan<LOG2N>;
     using DP = Duo4Plan<LOG2N>;
     constexpr int M = DP::M, N = DP::N, R = DP::R, G = DP::G, ROW = DP::ROW;
@@ -125,10 +154,21 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
             sm4[DP::OFF_TW1 + i] = make_float4(ta.x, ta.y, tb.x, tb.y);
         }
     }
-    __syncthreads();
+    [[maybe_unused]] float2* const sacc =
+        reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(sm4) + (DP::SMEM + 15) / 16 * 16) + tid;    // [slot][NT]
+    [[maybe_unused]] unsigned tacc = 0;
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) {
+        __shared__ unsigned tmem_base_s;
+        tacc = tm_alloc_cta<DP::TMEM_COLS>(&tmem_base_s, tid);
+    } else
+#endif
+    {
+        __syncthreads();
+    }
 
     const int kout = p.kmax - p.kmin + 1;
-    EpiDuo<MODE> epi;
+    typename std::conditional<SUM != 0, EpiDuoRec<2 * R + 1>, EpiDuo<MODE>>::type epi;
     epi.kout = kout;
     epi.floor = p.db_floor;
     epi.kmin = p.kmin;
@@ -157,13 +197,34 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
     while (u_next < p.n_units) {
         const long long u = u_next;
         u_next = dyn ? draw() : u + (long long)gridDim.x * DP::FPC;
-        const long long b = u / p.units_per_signal;
+        long long b = u / p.units_per_signal;
         const int c = (int)(u - b * p.units_per_signal);
-        const int f_begin = c * p.chunk_frames;
-        const int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
-        const Tin* const xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop +
-                              2 * (s + R * t);
-        float* const ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
+        int f_begin = c * p.chunk_frames;
+        int f_end = (f_begin + p.chunk_frames < p.nframes) ? f_begin + p.chunk_frames : p.nframes;
+        [[maybe_unused]] int blk = 0, nsweeps = 1;
+        if constexpr (SUM != 0) {
+            // unit = (sweep block, duo c), the duo index fastest; the "run" is the one duo (frames 2 c, 2 c + 1) of
+            // the block's first sweep, and the loop below walks the sweeps instead of the frames
+            blk = (int)b;
+            f_begin = 2 * c;
+            f_end = (f_begin + 2 < p.nframes) ? f_begin + 2 : p.nframes;
+            b = (long long)blk * p.acc_rows;
+            nsweeps = (int)((b + p.acc_rows < p.acc_batch) ? p.acc_rows : p.acc_batch - b);
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tm_st4(tacc + 4 * i, 0.f, 0.f, 0.f, 0.f);
+                tm_st2(tacc + 32, 0.f, 0.f);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int i = 0; i < DP::ACC_SLOTS; ++i) sacc[i * DP::NT] = cmk(0.f, 0.f);
+            }
+        }
+        const Tin* xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop +
+                        2 * (s + R * t);
+        float* ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
 
         // raw samples of the duo: slot i <-> complex index s + R (t + 16 i) relative to frame f;
         // slots 16.. belong to frame B only (without a frame B they re-read the previous S slots)
@@ -175,7 +236,7 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
             for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xf : xfB) + SLOT * i);
         }
 
-        for (int f = f_begin; f < f_end; f += 2) {
+        for (int f = f_begin, it = 0; (SUM != 0) ? (it < nsweeps) : (f < f_end); f += (SUM != 0 ? 0 : 2), ++it) {
             epi.actA = true;
             epi.actB = f + 1 < f_end;
             epi.rowA = ob + (long long)f * kout;
@@ -254,7 +315,13 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
             }
 
             // ---- next duo (frames f+2, f+3): keep the overlap, prefetch the 2 S new slots ----
-            {
+            if constexpr (SUM != 0) {            // the same duo of the next sweep: all 16 + S slots, one sweep ahead
+                if (it + 1 < nsweeps) xb += p.x_batch_stride;
+                const Tin* const xn = xb + (long long)f * p.hop;
+                const Tin* const xnB = xn - ((f + 1 < f_end) ? 0 : p.hop);
+#pragma unroll
+                for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(((i < 16) ? xn : xnB) + SLOT * i);
+            } else {
 #pragma unroll
                 for (int i = 0; i < KEEP; ++i) cur[i] = cur[i + 2 * S];
                 const int fa = (f + 2 < f_end) ? f + 2 : f_end - 1;
@@ -299,6 +366,20 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
             for (int cc = 0; cc < DP::TPT; ++cc) {
                 const int kap = j + G * cc;            // task id == kappa in [0, 128)
                 cpx2 U[R], V[R];
+                // SUM: the task's 2 R running sums (packed A, B), fetched while the butterflies run
+                [[maybe_unused]] float2 acc[2 * R + 1];
+                if constexpr (SUM != 0) {
+                    epi.nrec = 0;
+#ifndef B2S_EMU
+                    if constexpr (SUM == 2) {
+                        if (cc == 0) tm_st_wait();                     // the previous sweep's updates have landed
+#pragma unroll
+                        for (int i = 0; i < R; ++i)
+                            tm_ld4(tacc + 4 * (R * cc + i), acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+                        if (cc == 0) tm_ld2(tacc + 32, acc[2 * R].x, acc[2 * R].y);
+                    }
+#endif
+                }
                 if (kap != 0) {
                     const int kap2 = 256 - kap;
 #pragma unroll
@@ -345,7 +426,34 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
                         epi.pair(k, M - k, V[a], V[R - 1 - a], post(k), 1.0f);
                     }
                 }
+                if constexpr (SUM != 0) {
+                    // records 0 .. 2 R - 1 of this task -> slots 2 R cc + i; thread 0's task kap = 0 has one more
+                    // (the bins in the order of duo4_task_bins), kept in the last slot
+                    const bool extra = (cc == 0) && (j == 0);
+#ifndef B2S_EMU
+                    if constexpr (SUM == 2) {
+                        if (cc == 0) tm_ld_wait2(acc[2 * R].x, acc[2 * R].y);
+#pragma unroll
+                        for (int i = 0; i < R; ++i) {
+                            tm_ld_wait4(acc[2 * i].x, acc[2 * i].y, acc[2 * i + 1].x, acc[2 * i + 1].y);
+                            const float2 a0 = pk_add(acc[2 * i], epi.rec[2 * i]), a1 = pk_add(acc[2 * i + 1], epi.rec[2 * i + 1]);
+                            tm_st4(tacc + 4 * (R * cc + i), a0.x, a0.y, a1.x, a1.y);
+                        }
+                        if (cc == 0) {
+                            const float2 ax = extra ? pk_add(acc[2 * R], epi.rec[2 * R]) : acc[2 * R];
+                            tm_st2(tacc + 32, ax.x, ax.y);
+                        }
+                    } else
+#endif
+                    {
+#pragma unroll
+                        for (int i = 0; i < 2 * R; ++i)
+                            sacc[(2 * R * cc + i) * DP::NT] = pk_add(sacc[(2 * R * cc + i) * DP::NT], epi.rec[i]);
+                        if (extra) sacc[(DP::ACC_SLOTS - 1) * DP::NT] = pk_add(sacc[(DP::ACC_SLOTS - 1) * DP::NT], epi.rec[2 * R]);
+                    }
+                }
             }
+            if constexpr (SUM != 0) ob += p.out_batch_stride;
             if constexpr (MODE == EPI_BAND) {
                 const float2 bs = duo4_group_sum<LOG2N>(epi.band, grp, j, red + 2 * DP::RED);
                 epi.band = cmk(0.f, 0.f);
@@ -355,7 +463,70 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(Duo4Plan<LOG2N>::NT, Duo4Plan<LOG2N>::MINB) st
                 }
             }
         }
+        if constexpr (SUM != 0) {
+            // ---- the block's partial sums: p.acc[blk][frame][bin], bins in the order the tasks put them ----
+            float2 a[DP::ACC_SLOTS];
+#ifndef B2S_EMU
+            if constexpr (SUM == 2) {
+                tm_st_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    tm_ld4(tacc + 4 * i, a[2 * i].x, a[2 * i].y, a[2 * i + 1].x, a[2 * i + 1].y);
+                    tm_ld_wait4(a[2 * i].x, a[2 * i].y, a[2 * i + 1].x, a[2 * i + 1].y);
+                }
+                tm_ld2(tacc + 32, a[16].x, a[16].y);
+                tm_ld_wait2(a[16].x, a[16].y);
+            } else
+#endif
+            {
+#pragma unroll
+                for (int i = 0; i < DP::ACC_SLOTS; ++i) a[i] = sacc[i * DP::NT];
+            }
+            const bool hasB = f_begin + 1 < p.nframes;
+            float* const sA = p.acc + ((long long)blk * p.nframes + f_begin) * (M + 1);
+            auto out = [&](int k, float2 v) {
+                sA[k] = v.x;
+                if (hasB) sA[M + 1 + k] = v.y;
+            };
+#pragma unroll
+            for (int cc = 0; cc < DP::TPT; ++cc) {
+                const int kap = j + G * cc;
+                if (kap != 0) {
+#pragma unroll
+                    for (int aa = 0; aa < R; ++aa) {
+                        const int k = kap + aa * 256;
+                        out(k, a[2 * R * cc + 2 * aa]);
+                        out(M - k, a[2 * R * cc + 2 * aa + 1]);
+                    }
+                } else {
+                    // thread 0 of the duo, task kap = 0: (0, M), (256 a, M - 256 a) for 2 a < R, M / 2,
+                    // (128 + 256 a, M - 128 - 256 a) for 2 a < R - 1 -- 2 R + 1 values, the last one in the spare slot
+                    int i = 0;
+                    auto nxt = [&]() -> float2 {
+                        const float2 v = (i < 2 * R) ? a[i] : a[DP::ACC_SLOTS - 1];
+                        ++i;
+                        return v;
+                    };
+                    out(0, nxt());
+                    out(M, nxt());
+#pragma unroll
+                    for (int aa = 1; 2 * aa < R; ++aa) {
+                        out(aa * 256, nxt());
+                        out(M - aa * 256, nxt());
+                    }
+                    out(M / 2, nxt());
+#pragma unroll
+                    for (int aa = 0; 2 * aa < R - 1; ++aa) {
+                        out(128 + aa * 256, nxt());
+                        out(M - 128 - aa * 256, nxt());
+                    }
+                }
+            }
+        }
     }
+#ifndef B2S_EMU
+    if constexpr (SUM == 2) tm_free_cta<DP::TMEM_COLS>(tacc, tid);
+#endif
     if (dyn) {      // the last CTA to finish re-arms the counters for the next launch that uses them
         __syncthreads();
         if (tid == 0) {

@@ -60,6 +60,20 @@ struct DuoCtaPlan {
 
 B2S_HD int phys4(int e) { return e + (e >> 4); }
 
+// real-FFT split of the bin pair (k, M - k) of both frames and its power: Z[k] = zk, Z[M-k] = zm, w = W_N^k
+B2S_DEVICE void duo_pair_power(cpx2 zk, cpx2 zm, float2 w, float sc, float2& pa, float2& pb) {
+    const cpx2 e{pk_add(zk.re, zm.re), pk_sub(zk.im, zm.im)};      // 2E = zk + conj(zm)
+    const cpx2 o{pk_add(zk.im, zm.im), pk_sub(zm.re, zk.re)};      // 2O = -i (zk - conj(zm))
+    const cpx2 t = c2mul(o, w);
+    const cpx2 a = c2add(e, t), bq = c2sub(e, t);
+    pa = pk_fma(a.re, a.re, pk_mul(a.im, a.im));
+    pb = pk_fma(bq.re, bq.re, pk_mul(bq.im, bq.im));
+    if (sc != 1.0f) {
+        pa = pk_muls(pa, sc);
+        pb = pk_muls(pb, sc);
+    }
+}
+
 template <int MODE>
 struct EpiDuo {
     float* rowA;        // frame A row (already offset by -kmin); frame B row is rowA + kout
@@ -84,16 +98,33 @@ struct EpiDuo {
     }
     // Z[k] = zk, Z[M-k] = zm, w = W_N^k; the window carries sqrt(scale/2), so |2 X|^2 is the PSD
     B2S_DEVICE void pair(int k, int mk, cpx2 zk, cpx2 zm, float2 w, float sc) {
-        const cpx2 e{pk_add(zk.re, zm.re), pk_sub(zk.im, zm.im)};      // 2E = zk + conj(zm)
-        const cpx2 o{pk_add(zk.im, zm.im), pk_sub(zm.re, zk.re)};      // 2O = -i (zk - conj(zm))
-        const cpx2 t = c2mul(o, w);
-        const cpx2 a = c2add(e, t), bq = c2sub(e, t);
-        float2 pa = pk_fma(a.re, a.re, pk_mul(a.im, a.im));
-        float2 pb = pk_fma(bq.re, bq.re, pk_mul(bq.im, bq.im));
-        if (sc != 1.0f) {
-            pa = pk_muls(pa, sc);
-            pb = pk_muls(pb, sc);
-        }
+        float2 pa, pb;
+        duo_pair_power(zk, zm, w, sc, pa, pb);
+        put(k, pa);
+        put(mk, pb);
+    }
+};
+
+// The plain epilogue that also keeps what it stored (SUM mode of b2s_duo4_kernel.cuh): the NREC packed power
+// values of a final-stage task, in the order they were put -- indices are compile-time after unrolling.
+template <int NREC>
+struct EpiDuoRec {
+    float* rowA;
+    int kout;
+    float floor;
+    float2 band;
+    int kmin, kmax, db;
+    bool actA, actB;
+    int nrec;
+    float2 rec[NREC];
+    B2S_DEVICE void put(int k, float2 p) {
+        if (actA) rowA[k] = p.x;
+        if (actB) rowA[k + kout] = p.y;
+        rec[nrec++] = p;
+    }
+    B2S_DEVICE void pair(int k, int mk, cpx2 zk, cpx2 zm, float2 w, float sc) {
+        float2 pa, pb;
+        duo_pair_power(zk, zm, w, sc, pa, pb);
         put(k, pa);
         put(mk, pb);
     }

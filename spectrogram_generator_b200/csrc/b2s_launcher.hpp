@@ -111,6 +111,8 @@ const void* duo_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
 
 // the SUM mode of the 256-point frame-duo kernel, slots = 2 / 4 / 8 / 16 (b2s_inst_sum.cu); nullptr if there is none
 const void* duo256_sum_kernel_for(int x_is_f64, int slots, int acc_tmem);
+// the SUM mode of the four-step frame-duo kernel, nperseg 2048 / 4096, slots = 2 / 4 / 8 (b2s_inst_sum4.cu)
+const void* duo4_sum_kernel_for(int log2n, int x_is_f64, int slots, int acc_tmem);
 // the SUM mode of the staged-sample pair kernel, nperseg 1024 (b2s_inst_sum.cu)
 const void* pair_sum_kernel_for(int x_is_f64, int acc_tmem);
 

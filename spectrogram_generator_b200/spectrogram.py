@@ -201,7 +201,7 @@ class Engine:
         x: CUDA tensor [B, n]; returns ``(S[B, nframes, nbins], post_scale * S.sum(0))`` -- the
         rows are bit-identical to :meth:`stft_psd`'s, the sum is added in a fixed order.  For the
         shapes of the sum-fused kernels (nperseg 512 with hop 64/128/256, nperseg 256 with any even
-        hop, nperseg 1024 with any hop that is a multiple of 4) the rows are written once and never
+        hop, nperseg 1024 with any hop that is a multiple of 4, nperseg 2048 with hop 256/512/1024) the rows are written once and never
         read back; other shapes run :meth:`stft_psd` followed by :meth:`batch_sum` inside the
         library.  ``sum_out``: any contiguous CUDA float32 tensor of nframes*nbins elements."""
         lib = _lib.load()

@@ -247,6 +247,38 @@ extern "C" int emu_stft_psd_sum(const void* x, int x_is_f64, long long batch, lo
         emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
         return blocks;
     }
+    if (nperseg == 2048 || nperseg == 4096) {      // (4096: emulator only -- the library does not ship it, b2s_inst_sum4.cu)
+        // the SUM mode of the four-step frame-duo kernel (sums in shared memory: the twin of the product's kernel)
+        const int s4 = duo4_slots(a);
+        if (s4 != 2 && s4 != 4 && s4 != 8) return -200;
+        StftParams p{};
+        const int fpc = nperseg == 2048 ? Duo4Plan<11>::FPC : Duo4Plan<12>::FPC;
+        const int blocks = plan_stft_sum(a, (long long)grid * fpc, max_blocks, p, err, 1);
+        if (blocks < 0) return blocks;
+        std::vector<float> tw;
+        make_tables(nperseg, tw);
+        p.tw = reinterpret_cast<const float2*>(tw.data());
+        std::vector<float> part((size_t)blocks * elems, std::nanf(""));
+        p.acc = part.data();
+        const long long need = (p.n_units + fpc - 1) / fpc;
+        const unsigned g = (unsigned)(need < grid ? need : grid);
+        auto run = [&](auto kern, int nt, size_t smem) { emu::launch(g, nt, smem, [&] { kern(p); }); };
+#define B2S_EMU_SUM4(L, T)                                                                                                  \
+        do {                                                                                                                 \
+            using DP = Duo4Plan<L>;                                                                                          \
+            if (s4 == 2) run(stft_psd_duo4_sum_kernel<L, T, 2, 1>, DP::NT, DP::SUM_SMEM);                                   \
+            else if (s4 == 4) run(stft_psd_duo4_sum_kernel<L, T, 4, 1>, DP::NT, DP::SUM_SMEM);                              \
+            else run(stft_psd_duo4_sum_kernel<L, T, 8, 1>, DP::NT, DP::SUM_SMEM);                                           \
+        } while (0)
+        if (nperseg == 2048) {
+            if (x_is_f64) B2S_EMU_SUM4(11, double); else B2S_EMU_SUM4(11, float);
+        } else {
+            if (x_is_f64) B2S_EMU_SUM4(12, double); else B2S_EMU_SUM4(12, float);
+        }
+#undef B2S_EMU_SUM4
+        emu_batch_sum(part.data(), elems, blocks, blocks, elems, sum_out, post_scale);
+        return blocks;
+    }
     if (nperseg == 256) {
         // the SUM mode of the 256-point frame-duo kernel (sums in shared memory: the twin of the product's kernel)
         using DP = Duo256Plan;

@@ -297,6 +297,32 @@ def test_sum_fused_duo256_kernel(emu, hop, detrend, nframes, batch, grid, max_bl
     assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused duo256 256/{hop}")
 
 
+@pytest.mark.parametrize("nperseg,hop,detrend", [(2048, 512, "constant"), (2048, 256, False), (2048, 1024, "constant"),
+                                                 (4096, 1024, "constant"), (4096, 2048, False)])
+@pytest.mark.parametrize("nframes,batch,grid,max_blocks", [(5, 5, 1, 64), (4, 7, 2, 3), (1, 3, 1, 2)])
+def test_sum_fused_duo4_kernel(emu, nperseg, hop, detrend, nframes, batch, grid, max_blocks):
+    """nperseg 2048 / 4096: the SUM mode of the four-step frame-duo kernel (a thread group keeps one duo and walks
+    over a block of sweeps; every thread keeps the sums of its own final-stage tasks): rows bit-identical to the
+    per-sweep kernel's, the sum equals the float64 sum of the rows to fp32 rounding whatever the split into sweep
+    blocks (odd frame counts, ragged last block); float64 samples likewise."""
+    n = nperseg + hop * (nframes - 1) + 4
+    x = signal(batch, n, hop + nframes + batch, dc=-2.0 if detrend else 0.0)
+    kw = dict(window=("tukey", 0.25), nperseg=nperseg, noverlap=nperseg - hop, detrend=detrend)
+    plan = plan_for(n, 20000.0, **kw)
+    assert plan.nframes == nframes
+    rows = emu.stft_psd(x, plan, chunk=2)
+    assert emu.last_family() == "duo4"
+    got, tot, blocks = emu.stft_psd_sum(x, plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert 1 <= blocks <= min(max_blocks, batch)
+    assert np.array_equal(got, rows)
+    want = 0.5 * rows.astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(tot, want, rtol=1e-6, atol=0)
+    got64, tot64, _ = emu.stft_psd_sum(x.astype(np.float64), plan, post_scale=0.5, grid=grid, max_blocks=max_blocks)
+    assert np.array_equal(got64, rows) and np.array_equal(tot64, tot)
+    _, _, So = stft_oracle.spectrogram(x.astype(np.float64), fs=20000.0, **kw)
+    assert_parity(np.moveaxis(got, -1, -2), So, what=f"sum-fused duo4 {nperseg}/{hop}")
+
+
 def test_sum_fused_plan_fills_the_grid():
     """plan_stft_sum on BASELINE config 2 with a B200's resident groups: one round, 22 blocks of 46."""
     import ctypes

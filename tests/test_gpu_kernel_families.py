@@ -225,6 +225,9 @@ def test_large_batches_take_the_dynamic_schedule_and_stay_deterministic(nperseg,
     # nperseg 256: the SUM mode of the 256-point frame-duo kernel (S = 2 / 4 / 8, and S = 16 for every other even hop)
     (256, 64, 300, 11, 3), (256, 64, 1000, 622, 3), (256, 32, 77, 40, 3), (256, 128, 1000, 9, 3), (256, 224, 50, 9, 3),
     (256, 100, 20, 7, 3), (256, 256, 3, 1, 3),
+    # nperseg 2048 at hop 256 / 512 / 1024: the SUM mode of the four-step frame-duo kernel
+    (2048, 512, 500, 75, 4), (2048, 256, 33, 9, 4), (2048, 1024, 64, 6, 4), (2048, 512, 2, 1, 4),
+    (4096, 1024, 30, 7, 0), (2048, 300, 9, 5, 0),       # no fused kernel (4096: measured slower; 2048 at another hop)
     # nperseg 1024, rows 16-byte aligned: the SUM mode of the staged-sample pair kernel, any staged hop
     (1024, 256, 1000, 153, 2),      # the north-star target shape (1000 x 40 000 @ 1024/256) with its mean
     (1024, 896, 33, 7, 2), (1024, 1024, 64, 5, 2), (1024, 36, 9, 20, 2), (1024, 256, 2, 1, 2), (1024, 128, 300, 31, 2),
@@ -234,7 +237,7 @@ def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
     the sum equals the float64 sum of the rows to fp32 rounding and is the same on every run;
     float64 samples and a caller-provided flat sum buffer likewise."""
     rng = np.random.default_rng(nperseg + hop + B)
-    n = nperseg + hop * (nfr - 1) + {0: 2, 1: 3, 2: 4, 3: 2}[odd]
+    n = nperseg + hop * (nfr - 1) + {0: 2, 1: 3, 2: 4, 3: 2, 4: 2}[odd]
     x = _signal(rng, B, n, dc=-3.0)
     plan = sg.triage(n, 20000.0, "hann", nperseg, nperseg - hop, None, "constant", True, "density", "psd")
     assert plan.nframes == nfr
@@ -247,6 +250,8 @@ def test_rows_and_cross_sweep_sum_in_one_call(nperseg, hop, B, nfr, odd):
         assert _lib.last_kernel().startswith("stft_psd_pair_sum_kernel")
     if odd == 3:
         assert _lib.last_kernel().startswith("stft_psd_duo256_sum_kernel")
+    if odd == 4:
+        assert _lib.last_kernel().startswith("stft_psd_duo4_sum_kernel")
     assert torch.equal(S, rows)
     want = rows.double().sum(dim=0) / B
     torch.testing.assert_close(tot.double(), want, rtol=2e-6, atol=0)

@@ -131,7 +131,8 @@ def main():
                 shapes.append((1024, 100_000, nperseg, int(nperseg * (1 - ov))))
     if args.set == "mean":          # rows + cross-sweep sum in one call: fused kernels against per-sweep kernel + two-pass sum
         for sh in [(1000, 40000, 512, 128), (1000, 40000, 1024, 256), (1000, 40000, 1024, 128), (1000, 40000, 1024, 512),
-                   (1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 256, 64)]:
+                   (1000, 200_000, 1024, 896), (1000, 200_704, 1024, 1024), (1000, 40000, 256, 64),
+                   (1000, 40000, 2048, 512), (1000, 100_000, 2048, 512), (1000, 100_000, 4096, 1024), (1000, 100_000, 4096, 2048)]:
             for fused in (True, False):
                 print(json.dumps(time_mean(*sh, flush=flush, fused=fused)), flush=True)
     if args.set == "meandyn":       # the sum-fused kernels: sweep blocks and static / dynamic unit schedule
