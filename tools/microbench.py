@@ -146,6 +146,8 @@ def main():
                 print(json.dumps(r), flush=True)
         _lib.set_option("sum_blocks", 0)
         _lib.set_option("sum_dynamic", 0)
+    if args.set == "mean512":       # one shape, for ncu
+        print(json.dumps(time_mean(1000, 40000, 512, 128, iters=3, flush=flush)), flush=True)
     if args.set == "mean1024":      # one shape, for ncu
         print(json.dumps(time_mean(1000, 40000, 1024, 256, iters=3, flush=flush)), flush=True)
     for s in shapes:
