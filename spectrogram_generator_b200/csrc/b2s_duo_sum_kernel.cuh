@@ -191,6 +191,10 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
 
 
             // ---- the same duo of the next sweep: all 16 + S slots, one sweep ahead ----
+            // (Measured and dropped, round 2: loading the sweep when it is needed instead -- no 16 + S slots live
+            //  across the transform, 128 registers, FOUR CTAs per SM -- with nothing, an L2 or an L1 prefetch of
+            //  the next sweep's lines in their place: 0.171-0.175 ms against 0.169.  The kernel sits at the same
+            //  time with three or four warps per scheduler; profiles/r2_c2_duo_sum_full.ncu_summary.txt.)
             if (it + 1 < ntrip) xn += p.x_batch_stride;
 #pragma unroll
             for (int i = 0; i < NCUR; ++i) cur[i] = Loader<Tin>::ld2(xn + ((i < 16) ? 0 : offB) + 32 * i);
@@ -300,27 +304,29 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
         }
 
         // ---- the block's partial sums: p.acc[blk][frame][bin] ----
+        float4 a9[9];
 #ifndef B2S_EMU
-        if constexpr (ACC_TMEM) {        // through shared memory, so that the write-out below is the same code
-            tm_st_wait();
+        if constexpr (ACC_TMEM) {        // (straight from tensor memory: this kernel may be launched without the
+            tm_st_wait();                //  twin's shared-memory sums)
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) {
-                float4 a4;
-                tm_ld4(tacc + 4 * pp, a4.x, a4.y, a4.z, a4.w);
-                tm_ld_wait4(a4.x, a4.y, a4.z, a4.w);
-                sacc[pp * G] = a4;
+                tm_ld4(tacc + 4 * pp, a9[pp].x, a9[pp].y, a9[pp].z, a9[pp].w);
+                tm_ld_wait4(a9[pp].x, a9[pp].y, a9[pp].z, a9[pp].w);
             }
-            float2 am;
-            tm_ld2(tacc + 32, am.x, am.y);
-            tm_ld_wait2(am.x, am.y);
-            *reinterpret_cast<float2*>(sacc + 8 * G) = am;
-        }
+            a9[8] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tm_ld2(tacc + 32, a9[8].x, a9[8].y);
+            tm_ld_wait2(a9[8].x, a9[8].y);
+        } else
 #endif
+        {
+#pragma unroll
+            for (int pp = 0; pp < 9; ++pp) a9[pp] = sacc[pp * G];
+        }
         if (uvalid) {
             float* const sA = p.acc + ((long long)blk * p.nframes + f) * KOUT;
 #pragma unroll
             for (int pp = 0; pp < 8; ++pp) {
-                const float4 a4 = sacc[pp * G];
+                const float4 a4 = a9[pp];
                 sA[t + 16 * pp] = a4.x;
                 sA[M - t - 16 * pp] = a4.z;
                 if (hasB) {
@@ -329,9 +335,8 @@ B2S_GLOBAL void B2S_LAUNCH_BOUNDS(DuoPlan::NT, DuoPlan::MINB) stft_psd_duo_sum_k
                 }
             }
             if (is0) {
-                const float2 am = *reinterpret_cast<const float2*>(sacc + 8 * G);
-                sA[M / 2] = am.x;
-                if (hasB) sA[KOUT + M / 2] = am.y;
+                sA[M / 2] = a9[8].x;
+                if (hasB) sA[KOUT + M / 2] = a9[8].y;
             }
         }
     }
