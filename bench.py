@@ -379,6 +379,8 @@ class ShapeBench:
                                 1000, 40_000, 1024, 256, iters=7))
         shapes.append(self.stft_mean("north-star target shape with its mean: 1000 x 40 000 per GPU @ 1024/256, per-sweep "
                                      "spectrograms + cross-sweep sum", 1000, 40_000, 1024, 256))
+        shapes.append(self.stft_mean("the same batch @ 256/64, per-sweep spectrograms + cross-sweep sum", 1000, 40_000, 256, 64))
+        shapes.append(self.stft_mean("the same batch @ 2048/512, per-sweep spectrograms + cross-sweep sum", 1000, 40_000, 2048, 512))
         shapes.append(self.stft("north-star target, the reference's own call form (PlotEngine.py:113: Tukey(0.25), "
                                 "noverlap = nperseg//8, GUI default nperseg 1024), 1000 x 200 000 per GPU",
                                 1000, 200_000, 1024, 896, window=("tukey", .25), iters=5))
