@@ -44,7 +44,10 @@ struct Duo4Plan {
     static constexpr int RED = (G > 32) ? G / 32 : 1;    // warps per duo
     static constexpr int TPT = 128 / G;                  // final tasks per thread
     static constexpr int ROW = 17;
-    static constexpr int BUF = 16 * ROW;                 // float4 slots per sub-transform buffer
+    // float4 slots per sub-transform buffer: 16 rows of ROW, + 8 / R so that the R buffers of a duo start 8 / R
+    // quarter-bank-groups apart -- the pass-0 results are written by threads that hold R CONSECUTIVE sub-transforms
+    // (see "thread <-> point" below), and a quarter-warp of their 128-bit stores must not meet in a bank
+    static constexpr int BUF = 16 * ROW + 8 / R;
     // shared memory (float4 units): window taps [8][G] (slots 2j, 2j+1 of thread g), pass-1
     // twiddles [8][16], the NSUB exchange buffers, reduction slots
     static constexpr int OFF_WIN = 0;
@@ -118,10 +121,19 @@ B2S_DEVICE void stft_psd_duo4_body(const StftParams& p) {
     const int tid = (int)threadIdx.x;
     const int grp = tid / G;                             // duo inside the CTA
     const int j = tid - grp * G;                         // thread inside the duo
-    const int s = j >> 4;                                // sub-transform
+    // thread <-> point.  From the transpose on, thread j is lane t = j & 15 of sub-transform s = j >> 4 (16 lanes own a
+    // sub-transform, as the 512-point kernel owns its frame).  BEFORE it -- loads, detrend, window, the in-lane
+    // radix-16 over the slots -- any assignment works, and thread j takes sub-transform sL = j % R, row tL = j / R:
+    // its slot i is complex point sL + R (tL + 16 i) = j + G i, so the G threads of a duo read G CONSECUTIVE points
+    // (a warp: 256 contiguous bytes) instead of 16 points R apart per half-warp.  The pass-0 results change hands in
+    // the transpose buffer anyway.  (Round 2; before: 8 wavefronts per LDG.64 at nperseg 4096, 4 at 2048.)
+    const int s = j >> 4;                                // sub-transform (transpose read side, pass 1, final stage)
     const int t = j & 15;                                // lane inside the sub-transform
+    const int sL = j & (R - 1);                          // sub-transform and row of the points this thread LOADS
+    const int tL = j / R;
     float4* const bufs = sm4 + DP::OFF_BUF + (grp * R) * DP::BUF;    // the duo's R buffers
     float4* const buf = bufs + s * DP::BUF;
+    float4* const bufL = bufs + sL * DP::BUF;
     float4* const red = sm4 + DP::OFF_RED + grp * (3 * DP::RED + 1);
     float2* const stab = reinterpret_cast<float2*>(sm4 + DP::TOTAL);
     auto fin = [&](int i) -> float2 {            // W_M^(r kap) at (r - 1) * 256 + kap
@@ -143,7 +155,7 @@ B2S_DEVICE void stft_psd_duo4_body(const StftParams& p) {
         const float2* w2 = reinterpret_cast<const float2*>(p.window);
         for (int i = tid; i < 8 * G; i += DP::NT) {
             const int jj = i / G, g = i - jj * G;
-            const int n0 = (g >> 4) + R * ((g & 15) + 16 * (2 * jj));         // slot 2 jj of thread g
+            const int n0 = g + G * (2 * jj);                                  // slot 2 jj of thread g: point g + G i
             const float2 wa = __ldg(w2 + n0), wb = __ldg(w2 + n0 + 16 * R);
             sm4[DP::OFF_WIN + i] = make_float4(wa.x * csc, wa.y * csc, wb.x * csc, wb.y * csc);
         }
@@ -222,8 +234,7 @@ B2S_DEVICE void stft_psd_duo4_body(const StftParams& p) {
                 for (int i = 0; i < DP::ACC_SLOTS; ++i) sacc[i * DP::NT] = cmk(0.f, 0.f);
             }
         }
-        const Tin* xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop +
-                        2 * (s + R * t);
+        const Tin* xb = reinterpret_cast<const Tin*>(p.x) + b * p.x_batch_stride + p.frame0 * (long long)p.hop + 2 * j;
         float* ob = p.out + b * p.out_batch_stride - ((MODE == EPI_BAND) ? 0 : p.kmin);
 
         // raw samples of the duo: slot i <-> complex index s + R (t + 16 i) relative to frame f;
@@ -337,9 +348,9 @@ B2S_DEVICE void stft_psd_duo4_body(const StftParams& p) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const cpx2 z = v[perm16(q)];
-                buf[ROW * t + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
+                bufL[ROW * tL + q] = make_float4(z.re.x, z.re.y, z.im.x, z.im.y);
             }
-            __syncwarp();
+            duo_group_sync<G>(grp);              // the rows of a sub-transform come from R different warps
 #pragma unroll
             for (int tt = 0; tt < 16; ++tt) {
                 const float4 q4 = buf[ROW * tt + t];
