@@ -512,7 +512,8 @@ def run_gpu(args):
         try:
             from spectrogram_generator_b200.distributed import PeerMeanReducer
             peer = PeerMeanReducer(plan.nframes * plan.nbins, dev, overlap=overlap,
-                                   coresident=os.environ.get("B2S_BENCH_PEER_CORESIDENT", "0") == "1")
+                                   coresident=os.environ.get("B2S_BENCH_PEER_CORESIDENT", "0") == "1",
+                                   nbuf=int(os.environ.get("B2S_BENCH_PEER_NBUF", "3")))
         except Exception as e:          # pragma: no cover
             if rank == 0:
                 print(f"peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
@@ -541,13 +542,13 @@ def run_gpu(args):
             return mean_buf
         return eng.batch_sum(S, 1.0 / total_sweeps, out=mean_buf)
 
-    peer_out = [torch.empty(plan.nframes * plan.nbins, dtype=torch.float32, device=dev) for _ in range(4)]
+    peer_out = [torch.empty(plan.nframes * plan.nbins, dtype=torch.float32, device=dev) for _ in range(16)]
 
     def reduce_mean():
         if peer is not None:
             if not fused:
                 eng.batch_sum(S, 1.0, out=peer.partial())
-            return peer.reduce(1.0 / total_sweeps, out=peer_out[peer.epoch & 3])
+            return peer.reduce(1.0 / total_sweeps, out=peer_out[peer.epoch & 15])
         mean = partial_mean()                            # partial mean of this rank's sweeps
         if world > 1 and mode == "sync":
             dist.all_reduce(mean)                        # sum of partial means == global mean

@@ -182,7 +182,8 @@ class PeerMeanReducer:
     then ``mean = r.reduce(1.0 / total_sweeps)``.
     """
 
-    def __init__(self, elems: int, device, group=None, overlap: bool = False, coresident: bool = False):
+    def __init__(self, elems: int, device, group=None, overlap: bool = False, coresident: bool = False,
+                 nbuf: Optional[int] = None):
         import ctypes
 
         import torch.distributed._symmetric_memory as symm_mem
@@ -203,7 +204,10 @@ class PeerMeanReducer:
         # four warps at a time, so even a one-warp CTA does not fit the 1024 registers three STFT CTAs leave and
         # displaces one of them on every SM (0.176 -> 0.194 ms per step).  Off by default.
         self.coresident = bool(coresident)
-        self.nbuf = 3 if self.overlap else 2
+        # nbuf > 3 (overlap mode): the launching stream may run up to nbuf - 2 steps ahead of the slowest rank before it
+        # has to wait for a slot, so the step-to-step jitter of the ranks is not paid at every step (each step would
+        # otherwise cost the slowest rank's time of that step); the reduces themselves stay in lockstep on the side stream.
+        self.nbuf = (max(3, int(nbuf)) if nbuf else 3) if self.overlap else 2
         self.stride = (self.elems + 3) // 4 * 4           # every slot 16-byte aligned: 128-bit peer loads
         self.buf = symm_mem.empty(self.nbuf * self.stride, dtype=torch.float32, device=self.device)
         self.handle = symm_mem.rendezvous(self.buf, group)
@@ -219,8 +223,9 @@ class PeerMeanReducer:
                 self.side = torch.cuda.Stream(priority=-1)       # its few CTAs go first when slots free up
                 # events are reused round-robin (a wait captures the record that precedes it): the step
                 # loop must stay cheap on the host, one step is ~0.17 ms of GPU time
-                self._ev_ready = [torch.cuda.Event() for _ in range(4)]
-                self._ev_done = [torch.cuda.Event() for _ in range(4)]
+                self._nev = self.nbuf + 2
+                self._ev_ready = [torch.cuda.Event() for _ in range(self._nev)]
+                self._ev_done = [torch.cuda.Event() for _ in range(self._nev)]
         self.handle.barrier()                  # pads and buffers exist on every rank before the first kernel
 
     def _slot(self, epoch: int) -> int:
@@ -231,8 +236,10 @@ class PeerMeanReducer:
         current stream first waits until the slot's previous content has been read by every peer."""
         nxt = self.epoch + 1
         if self.overlap:
-            ev = self._done.pop(nxt - 2, None)
-            if ev is not None:
+            # slot nxt % nbuf held epoch nxt - nbuf; every peer has read it once this rank's reduce(nxt - nbuf + 1) is
+            # done.  Normally that was several steps ago: then nothing is put into the stream at all
+            ev = self._done.pop(nxt - (self.nbuf - 1), None)
+            if ev is not None and not ev.query():
                 torch.cuda.current_stream(self.device).wait_event(ev)
         k = self._slot(nxt)
         return self.buf[k * self.stride:k * self.stride + self.elems]
@@ -252,7 +259,7 @@ class PeerMeanReducer:
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             if self.overlap:
-                ready = self._ev_ready[self.epoch & 3]
+                ready = self._ev_ready[self.epoch % self._nev]
                 ready.record(cur)
                 self.side.wait_event(ready)
                 stream = self.side
@@ -265,7 +272,7 @@ class PeerMeanReducer:
             if self.overlap:
                 if not caller_out:
                     out.record_stream(self.side)
-                done = self._ev_done[self.epoch & 3]
+                done = self._ev_done[self.epoch % self._nev]
                 done.record(self.side)
                 self._done[self.epoch] = done
         return out
