@@ -397,7 +397,8 @@ def _to_host(d: torch.Tensor, dtype) -> np.ndarray:
 
 
 _PIPE_CHUNK_BYTES = 32 << 20       # output bytes per pipeline stage
-_PIPE_RAMP_DIV = 16                # the first stage is 1/_PIPE_RAMP_DIV of a full one, the next ones double
+_PIPE_RAMP_DIV = 16                # the first stage is 1/_PIPE_RAMP_DIV of a full one ...
+_PIPE_RAMP_GROWTH = 2.0            # ... and every next one this many times the one before, up to a full stage
 
 
 class _Streams:
@@ -465,7 +466,7 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
             while b < B:
                 items.append((b, min(B, b + cur_step), 0, F))
                 b += cur_step
-                cur_step = min(step, cur_step * 2)
+                cur_step = min(step, max(cur_step + 1, int(cur_step * _PIPE_RAMP_GROWTH)))
         else:
             fstep = max(1, _PIPE_CHUNK_BYTES // (kout * 4))
             for b in range(B):
@@ -473,7 +474,7 @@ def _host_pipeline(x2d: np.ndarray, plan: Plan, dev, out_dtype, *, per_sweep=Tru
                 while f < F:
                     items.append((b, b + 1, f, min(F, f + cur_step)))
                     f += cur_step
-                    cur_step = min(fstep, cur_step * 2)
+                    cur_step = min(fstep, max(cur_step + 1, int(cur_step * _PIPE_RAMP_GROWTH)))
         if len(items) == 1:
             # one stage: nothing to overlap -- copy in, compute, copy out on the caller's stream
             x_d.copy_(h_in, non_blocking=pinned)

@@ -72,12 +72,11 @@ for mb in (8, 16, 32, 64, 128):
     print(f"chunk {mb:3d} MB: copy-only pipeline {t_copy:6.3f} ms   api {t_api:6.3f} ms   {x.size / t_api / 1e6:6.2f} Gsamples/s")
 
 sp._PIPE_CHUNK_BYTES = 32 << 20
-for div in (1, 2, 4, 8, 16, 32):
-    sp._PIPE_RAMP_DIV = div
-    t_api = timeit(lambda: sg.mean_spectrogram(xp, fs=fs, return_per_sweep=True, out=out, **kw), reps=12)
-    print(f"ramp 1/{div:2d}: api {t_api:6.3f} ms")
-sp._PIPE_RAMP_DIV = 16
-# fixed overhead of a call: two sweeps (single stage: copy in, kernel, copy out, sync)
-x2 = sg.pinned_empty((2, n), np.float32); x2[...] = x[:2]
-o2 = sg.pinned_empty((2, F, K), np.float32)
-print("two sweeps, whole call ms", round(timeit(lambda: sg.mean_spectrogram(x2, fs=fs, return_per_sweep=True, out=o2, **kw), reps=50), 4))
+call = lambda: sg.mean_spectrogram(xp, fs=fs, return_per_sweep=True, out=out, **kw)
+for rnd in range(2):
+    for div, growth in [(16, 2.0), (16, 1.5), (16, 1.25), (32, 1.5), (8, 1.5), (16, 1.5), (16, 2.0)]:
+        sp._PIPE_RAMP_DIV, sp._PIPE_RAMP_GROWTH = div, growth
+        print(f"round {rnd} ramp 1/{div:2d} x {growth}: api {timeit(call, reps=12):6.3f} ms")
+for mb, div, growth in [(16, 16, 1.5), (64, 32, 1.5), (32, 16, 2.0)]:
+    sp._PIPE_CHUNK_BYTES, sp._PIPE_RAMP_DIV, sp._PIPE_RAMP_GROWTH = mb << 20, div, growth
+    print(f"chunk {mb} MB ramp 1/{div} x {growth}: api {timeit(call, reps=12):6.3f} ms")
